@@ -1,0 +1,12 @@
+// Internal interface between the encoder front (encoder.cu) and the tensor-core plan (conv_tc.cu).
+#pragma once
+#include "common.cuh"
+#include <vector>
+namespace hp3d {
+int fold_conv_bn(const hp3d_conv_bn& c, float eps, int cin_pad, std::vector<float>& w_khwc, std::vector<float>& bias);
+int encoder_tc_create(const hp3d_encoder_weights* w, void** out);
+void encoder_tc_destroy(void* p);
+size_t encoder_tc_workspace_bytes(const void* p, int B, int H, int W);
+int encoder_tc_forward(const void* p, const float* x_nchw, int B, int H, int W, float* feats, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream);
+}  // namespace hp3d

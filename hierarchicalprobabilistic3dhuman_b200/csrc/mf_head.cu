@@ -1,0 +1,313 @@
+// Hierarchical matrix-Fisher distribution head for sm_100a.
+//
+// Replaces reference models/poseMF_shapeGaussian_net.py:95-160. The reference runs 23 sequential
+// joint steps, each with two tiny GEMMs, a device->host copy, a LAPACK SVD on the CPU and five
+// host->device copies (:137-141). Here:
+//   stage 1 (batch-parallel fp32 GEMMs): x = ELU(fc1 f); shape/glob/cam heads; embed = ELU(fc_embed
+//     [f | shape | glob | cam]); and -- because the first layer of every joint MLP is linear in its
+//     concatenated input -- the embed part of ALL 23 first layers at once:
+//     pre[b][j][:] = W1_j[:, :256] embed_b + b1_j   (one (B x 256) x (256 x 2944) GEMM).
+//   stage 2 (one CTA per image, no host round trips): walk the joints in index order (parents
+//     precede children); hidden = ELU(pre_j + W1_j[:, 256:] [U_p | S_p | mode](ancestors));
+//     F = W2_j hidden + b2_j + delta I; in-register LAPACK-convention 3x3 SVD (svd3.h); proper
+//     factors (:148-150); mode = U_p V_p^T (:152); ancestors' state stays in shared memory.
+#include "common.cuh"
+#include "svd3.h"
+#include <vector>
+
+using namespace hp3d;
+
+namespace {
+constexpr int FEAT = 512, FC1 = 512, EMBED = 256, HID = 128, NSHAPE = 20, NGLOB = 6, NCAM = 3;
+constexpr int CAT = FEAT + NSHAPE + NGLOB + NCAM;   // 541
+constexpr int CATP = 544;                            // padded row pitch
+constexpr int PRE = NBJ * HID;                       // 2944
+constexpr int MAX_ANC = 8;
+}
+
+struct hp3d_head {
+  float *fc1_wt = nullptr, *fc1_b = nullptr;         // [512][512] (in, out)
+  float *small_wt = nullptr, *small_b = nullptr;     // [512][29] heads (shape|glob|cam) + bias with init folded
+  float *embed_wt = nullptr, *embed_b = nullptr;     // [541][256]
+  float *pre_wt = nullptr, *pre_b = nullptr;         // [256][2944]
+  float *anc_wt = nullptr;                           // concatenated [21*n_anc[j]][128] blocks
+  float *w2 = nullptr, *b2 = nullptr;                // [23][9][128], [23][9]
+  int anc_off[NBJ];                                  // float offset of joint j's block in anc_wt
+  int n_anc[NBJ];
+  int anc[NBJ][MAX_ANC];
+  float delta_i;
+};
+
+struct HeadTree {
+  int anc_off[NBJ];
+  int8_t n_anc[NBJ];
+  int8_t anc[NBJ][MAX_ANC];
+};
+
+namespace {
+
+// y[b][o] = act(sum_i x[b][i] Wt[i][o] + bias[o]); 8 batch rows x 32 outputs per CTA.
+template <int ACT>  // 0 none, 1 ELU
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, int ldx, int K,
+                                                     const float* __restrict__ Wt, const float* __restrict__ bias,
+                                                     int O, float* __restrict__ y, int ldy, int B) {
+  extern __shared__ float sx[];   // [8][K]
+  const int b0 = blockIdx.y * 8, o = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
+  for (int t = threadIdx.x; t < 8 * K; t += 256) {
+    const int rr = t / K, kk = t - rr * K;
+    sx[t] = (b0 + rr < B) ? x[(size_t)(b0 + rr) * ldx + kk] : 0.f;
+  }
+  __syncthreads();
+  if (o >= O || b0 + r >= B) return;
+  const float* xr = sx + r * K;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int k = 0;
+  for (; k + 4 <= K; k += 4) {
+    a0 = fmaf(xr[k], Wt[(size_t)k * O + o], a0);
+    a1 = fmaf(xr[k + 1], Wt[(size_t)(k + 1) * O + o], a1);
+    a2 = fmaf(xr[k + 2], Wt[(size_t)(k + 2) * O + o], a2);
+    a3 = fmaf(xr[k + 3], Wt[(size_t)(k + 3) * O + o], a3);
+  }
+  for (; k < K; ++k) a0 = fmaf(xr[k], Wt[(size_t)k * O + o], a0);
+  float v = (a0 + a1) + (a2 + a3) + bias[o];
+  if (ACT == 1) v = v > 0.f ? v : expm1f(v);
+  y[(size_t)(b0 + r) * ldy + o] = v;
+}
+
+// cat[b] = [feats_b | shape | glob | cam]; also writes the user-facing shape/glob/cam tensors.
+__global__ void __launch_bounds__(256) pack_cat_kernel(const float* __restrict__ feats,
+                                                       const float* __restrict__ small, int B,
+                                                       float* __restrict__ cat, float* __restrict__ shape_params,
+                                                       float* __restrict__ glob, float* __restrict__ cam) {
+  const int b = blockIdx.x;
+  for (int t = threadIdx.x; t < CAT; t += 256) {
+    float v;
+    if (t < FEAT) v = feats[(size_t)b * FEAT + t];
+    else {
+      const int s = t - FEAT;
+      v = small[(size_t)b * 32 + s];
+      if (s < NSHAPE) shape_params[(size_t)b * NSHAPE + s] = v;
+      else if (s < NSHAPE + NGLOB) glob[(size_t)b * NGLOB + (s - NSHAPE)] = v;
+      else cam[(size_t)b * NCAM + (s - NSHAPE - NGLOB)] = v;
+    }
+    cat[(size_t)b * CATP + t] = v;
+  }
+}
+
+__global__ void __launch_bounds__(HID) head_tree_kernel(const float* __restrict__ pre, const float* __restrict__ anc_wt,
+                                                        const float* __restrict__ w2, const float* __restrict__ b2,
+                                                        HeadTree tree, float delta_i, int B,
+                                                        const float* __restrict__ tUp, const float* __restrict__ tSp,
+                                                        const float* __restrict__ tMode, float* __restrict__ F,
+                                                        float* __restrict__ U, float* __restrict__ S,
+                                                        float* __restrict__ V, float* __restrict__ mode) {
+  __shared__ float sUp[NBJ][9], sSp[NBJ][3], sMode[NBJ][9];
+  __shared__ float sIn[21 * MAX_ANC];
+  __shared__ float sPart[HID / 32][9];
+  __shared__ float sF[9];
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  if (tUp) {   // teacher forcing: ancestors' inputs come from the given tensors
+    for (int i = t; i < NBJ * 9; i += HID) { sUp[i / 9][i % 9] = tUp[(size_t)b * NBJ * 9 + i]; sMode[i / 9][i % 9] = tMode[(size_t)b * NBJ * 9 + i]; }
+    for (int i = t; i < NBJ * 3; i += HID) sSp[i / 3][i % 3] = tSp[(size_t)b * NBJ * 3 + i];
+  }
+  __syncthreads();
+  for (int j = 0; j < NBJ; ++j) {
+    const int p = tree.n_anc[j];
+    // reference input layout (:126-130): [embed | U_p(anc 0..p-1) | S_p(anc ..) | mode(anc ..)]
+    for (int i = t; i < 21 * p; i += HID) {
+      float v;
+      if (i < 9 * p) v = sUp[tree.anc[j][i / 9]][i % 9];
+      else if (i < 12 * p) { const int q = i - 9 * p; v = sSp[tree.anc[j][q / 3]][q % 3]; }
+      else { const int q = i - 12 * p; v = sMode[tree.anc[j][q / 9]][q % 9]; }
+      sIn[i] = v;
+    }
+    __syncthreads();
+    float h = pre[(size_t)b * PRE + j * HID + t];
+    const float* wa = anc_wt + tree.anc_off[j];
+    for (int i = 0; i < 21 * p; ++i) h = fmaf(sIn[i], wa[i * HID + t], h);
+    h = h > 0.f ? h : expm1f(h);
+    // F = W2 h + b2 (+ delta I): per-warp partial dot products, then 9 threads finish
+    const float* w2j = w2 + (size_t)j * 9 * HID;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      float v = w2j[e * HID + t] * h;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) sPart[warp][e] = v;
+    }
+    __syncthreads();
+    if (t < 9) {
+      float v = b2[j * 9 + t];
+#pragma unroll
+      for (int w = 0; w < HID / 32; ++w) v += sPart[w][t];
+      if (t == 0 || t == 4 || t == 8) v += delta_i;
+      sF[t] = v;
+    }
+    __syncthreads();
+    if (t == 0) {
+      float Fm[9], Um[9], Sm[3], Vm[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) Fm[e] = sF[e];
+      svd3_lapack(Fm, Um, Sm, Vm);
+      const float du = det3(Um), dv = det3(Vm);
+      const size_t o9 = ((size_t)b * NBJ + j) * 9, o3 = ((size_t)b * NBJ + j) * 3;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) { F[o9 + e] = Fm[e]; U[o9 + e] = Um[e]; V[o9 + e] = Vm[e]; }
+      S[o3] = Sm[0]; S[o3 + 1] = Sm[1]; S[o3 + 2] = Sm[2];
+      float Up[9], Vp[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) { Up[e] = Um[e]; Vp[e] = Vm[e]; }
+      Up[2] *= du; Up[5] *= du; Up[8] *= du;
+      Vp[2] *= dv; Vp[5] *= dv; Vp[8] *= dv;
+      float Md[9];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          Md[r * 3 + c] = Up[r * 3] * Vp[c * 3] + Up[r * 3 + 1] * Vp[c * 3 + 1] + Up[r * 3 + 2] * Vp[c * 3 + 2];
+#pragma unroll
+      for (int e = 0; e < 9; ++e) mode[o9 + e] = Md[e];
+      if (!tUp) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) { sUp[j][e] = Up[e]; sMode[j][e] = Md[e]; }
+        sSp[j][0] = Sm[0]; sSp[j][1] = Sm[1]; sSp[j][2] = Sm[2] * (du * dv);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+std::vector<float> transpose_oi(const float* w, int O, int I, int ldo = -1) {   // [O][I] -> [I][ldo]
+  if (ldo < 0) ldo = O;
+  std::vector<float> t((size_t)I * ldo, 0.f);
+  for (int o = 0; o < O; ++o)
+    for (int i = 0; i < I; ++i) t[(size_t)i * ldo + o] = w[(size_t)o * I + i];
+  return t;
+}
+
+}  // namespace
+
+extern "C" int hp3d_head_create(const hp3d_head_weights* w, hp3d_head** out) {
+  HP3D_ARG(w && out, "null argument");
+  HP3D_ARG(w->fc1_w && w->fc1_b && w->fc_shape_w && w->fc_shape_b && w->fc_glob_w && w->fc_glob_b && w->fc_cam_w &&
+           w->fc_cam_b && w->fc_embed_w && w->fc_embed_b && w->fc_pose0_w && w->fc_pose0_b && w->fc_pose2_w &&
+           w->fc_pose2_b && w->init_glob && w->init_cam && w->parents, "null weight pointer");
+  hp3d_head* h = new hp3d_head();
+  h->delta_i = w->delta_i_weight;
+  // ancestors, nearest first (reference :14-21)
+  for (int j = 0; j < NBJ; ++j) {
+    int n = 0;
+    int ip = w->parents[j + 1] - 1;
+    while (ip >= 0) {
+      if (n >= MAX_ANC) { delete h; set_error("hp3d_head_create: kinematic chain deeper than %d", MAX_ANC); return -1; }
+      h->anc[j][n++] = ip;
+      ip = w->parents[ip + 1] - 1;
+    }
+    h->n_anc[j] = n;
+  }
+  int rc = 0;
+  {
+    auto t = transpose_oi(w->fc1_w, FC1, FEAT);
+    rc = rc ? rc : upload(&h->fc1_wt, t.data(), t.size());
+    rc = rc ? rc : upload(&h->fc1_b, w->fc1_b, FC1);
+  }
+  {
+    std::vector<float> t((size_t)FC1 * 32, 0.f), bb(32, 0.f);
+    for (int i = 0; i < FC1; ++i) {
+      for (int o = 0; o < NSHAPE; ++o) t[(size_t)i * 32 + o] = w->fc_shape_w[(size_t)o * FC1 + i];
+      for (int o = 0; o < NGLOB; ++o) t[(size_t)i * 32 + NSHAPE + o] = w->fc_glob_w[(size_t)o * FC1 + i];
+      for (int o = 0; o < NCAM; ++o) t[(size_t)i * 32 + NSHAPE + NGLOB + o] = w->fc_cam_w[(size_t)o * FC1 + i];
+    }
+    for (int o = 0; o < NSHAPE; ++o) bb[o] = w->fc_shape_b[o];
+    // glob = fc_glob(x) + init_glob (:106): keep the reference's rounding order (bias first, init added in-kernel)
+    for (int o = 0; o < NGLOB; ++o) bb[NSHAPE + o] = w->fc_glob_b[o];
+    for (int o = 0; o < NCAM; ++o) bb[NSHAPE + NGLOB + o] = w->fc_cam_b[o];
+    rc = rc ? rc : upload(&h->small_wt, t.data(), t.size());
+    rc = rc ? rc : upload(&h->small_b, bb.data(), bb.size());
+  }
+  {
+    auto t = transpose_oi(w->fc_embed_w, EMBED, CAT);
+    rc = rc ? rc : upload(&h->embed_wt, t.data(), t.size());
+    rc = rc ? rc : upload(&h->embed_b, w->fc_embed_b, EMBED);
+  }
+  {
+    std::vector<float> pw((size_t)EMBED * PRE), pb(PRE), aw, w2((size_t)NBJ * 9 * HID), b2(NBJ * 9);
+    for (int j = 0; j < NBJ; ++j) {
+      const int in_dim = EMBED + 21 * h->n_anc[j];
+      const float* W = w->fc_pose0_w[j];
+      for (int o = 0; o < HID; ++o) {
+        for (int i = 0; i < EMBED; ++i) pw[(size_t)i * PRE + j * HID + o] = W[(size_t)o * in_dim + i];
+        pb[j * HID + o] = w->fc_pose0_b[j][o];
+      }
+      h->anc_off[j] = (int)aw.size();
+      aw.resize(aw.size() + (size_t)21 * h->n_anc[j] * HID);
+      for (int i = 0; i < 21 * h->n_anc[j]; ++i)
+        for (int o = 0; o < HID; ++o) aw[(size_t)h->anc_off[j] + (size_t)i * HID + o] = W[(size_t)o * in_dim + EMBED + i];
+      for (int e = 0; e < 9 * HID; ++e) w2[(size_t)j * 9 * HID + e] = w->fc_pose2_w[j][e];
+      for (int e = 0; e < 9; ++e) b2[j * 9 + e] = w->fc_pose2_b[j][e];
+    }
+    if (aw.empty()) aw.push_back(0.f);
+    rc = rc ? rc : upload(&h->pre_wt, pw.data(), pw.size());
+    rc = rc ? rc : upload(&h->pre_b, pb.data(), pb.size());
+    rc = rc ? rc : upload(&h->anc_wt, aw.data(), aw.size());
+    rc = rc ? rc : upload(&h->w2, w2.data(), w2.size());
+    rc = rc ? rc : upload(&h->b2, b2.data(), b2.size());
+  }
+  // init_glob / init_cam are added after the bias like the reference does: keep them as a second bias
+  {
+    std::vector<float> init(32, 0.f);
+    for (int o = 0; o < NGLOB; ++o) init[NSHAPE + o] = w->init_glob[o];
+    for (int o = 0; o < NCAM; ++o) init[NSHAPE + NGLOB + o] = w->init_cam[o];
+    // fold: (acc + bias) + init -- done by storing bias and init separately would need another pass; the
+    // kernel adds `bias` once, so pre-add here in fp32 (difference <= 1 ulp of the sum, far below 1e-4).
+    std::vector<float> bb(32);
+    cudaMemcpy(bb.data(), h->small_b, 32 * sizeof(float), cudaMemcpyDeviceToHost);
+    for (int o = 0; o < 32; ++o) bb[o] += init[o];
+    cudaMemcpy(h->small_b, bb.data(), 32 * sizeof(float), cudaMemcpyHostToDevice);
+  }
+  if (rc) { hp3d_head_destroy(h); return rc; }
+  *out = h;
+  return 0;
+}
+
+extern "C" void hp3d_head_destroy(hp3d_head* h) {
+  if (!h) return;
+  cudaFree(h->fc1_wt); cudaFree(h->fc1_b); cudaFree(h->small_wt); cudaFree(h->small_b); cudaFree(h->embed_wt);
+  cudaFree(h->embed_b); cudaFree(h->pre_wt); cudaFree(h->pre_b); cudaFree(h->anc_wt); cudaFree(h->w2); cudaFree(h->b2);
+  delete h;
+}
+
+extern "C" size_t hp3d_head_workspace_bytes(const hp3d_head*, int B) {
+  if (B <= 0) return 0;
+  return (size_t)B * (FC1 + 32 + CATP + EMBED + PRE) * sizeof(float);
+}
+
+extern "C" int hp3d_head_forward(const hp3d_head* h, const float* feats, int B, float* F, float* U, float* S, float* V,
+                                 float* mode, float* shape_params, float* glob, float* cam, const float* tUp,
+                                 const float* tSp, const float* tMode, void* workspace, size_t workspace_bytes,
+                                 void* stream_) {
+  HP3D_ARG(h && feats && F && U && S && V && mode && shape_params && glob && cam && workspace, "null argument");
+  HP3D_ARG(B > 0, "B must be > 0");
+  HP3D_ARG(workspace_bytes >= hp3d_head_workspace_bytes(h, B), "workspace too small");
+  HP3D_ARG((tUp == nullptr) == (tSp == nullptr) && (tUp == nullptr) == (tMode == nullptr), "teacher tensors must be given together");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  float* x = (float*)workspace;
+  float* small = x + (size_t)B * FC1;
+  float* cat = small + (size_t)B * 32;
+  float* embed = cat + (size_t)B * CATP;
+  float* pre = embed + (size_t)B * EMBED;
+  const int gy = cdiv(B, 8);
+  linear_kernel<1><<<dim3(cdiv(FC1, 32), gy), 256, 8 * FEAT * sizeof(float), stream>>>(feats, FEAT, FEAT, h->fc1_wt, h->fc1_b, FC1, x, FC1, B);
+  linear_kernel<0><<<dim3(1, gy), 256, 8 * FC1 * sizeof(float), stream>>>(x, FC1, FC1, h->small_wt, h->small_b, 32, small, 32, B);
+  pack_cat_kernel<<<B, 256, 0, stream>>>(feats, small, B, cat, shape_params, glob, cam);
+  linear_kernel<1><<<dim3(cdiv(EMBED, 32), gy), 256, 8 * CAT * sizeof(float), stream>>>(cat, CATP, CAT, h->embed_wt, h->embed_b, EMBED, embed, EMBED, B);
+  linear_kernel<0><<<dim3(cdiv(PRE, 32), gy), 256, 8 * EMBED * sizeof(float), stream>>>(embed, EMBED, EMBED, h->pre_wt, h->pre_b, PRE, pre, PRE, B);
+  HeadTree tree;
+  for (int j = 0; j < NBJ; ++j) {
+    tree.anc_off[j] = h->anc_off[j];
+    tree.n_anc[j] = (int8_t)h->n_anc[j];
+    for (int a = 0; a < MAX_ANC; ++a) tree.anc[j][a] = (int8_t)(a < h->n_anc[j] ? h->anc[j][a] : 0);
+  }
+  head_tree_kernel<<<B, HID, 0, stream>>>(pre, h->anc_wt, h->w2, h->b2, tree, h->delta_i, B, tUp, tSp, tMode, F, U, S, V, mode);
+  return launch_status("head kernels");
+}

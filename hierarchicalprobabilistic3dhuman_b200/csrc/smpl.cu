@@ -1,0 +1,513 @@
+// SMPL forward for sm_100a: shape blend -> pose-corrective blend -> fused FK + linear blend skinning
+// (+ 90-joint epilogue), and the per-vertex sample statistics.
+//
+// Replaces reference models/smpl_official.py:27-41 and the smplx 0.1.26 lbs() it calls
+// (SURVEY.md §8c steps 1-9). Data layout in HBM (all fp32):
+//   v_shaped  [Mb][20672]   one row per distinct shape (pitch padded to 16 B)
+//   v_posed   [M][20670]    written by the blend stage, read once by the LBS kernel
+//   vertices  [M][6890][3]  the reference's output layout; joints [M][90][3]
+// Model constants are repacked once at create time:
+//   shapedirs -> [10][20672]; posedirs -> [207][20672] (row pitch padded for float4 loads);
+//   J_regressor is folded into J_template [24*3] + J_shapedirs [24*3][10] (J is linear in beta);
+//   lbs_weights -> per-vertex top-K (idx,w) in SoA [K][6890] (K = max nnz, 4 for SMPL);
+//   the three extra joint regressors -> one CSR (255 nnz).
+#include "common.cuh"
+#include <vector>
+#include <algorithm>
+#include <math.h>
+
+using namespace hp3d;
+
+struct SmplTree {
+  int8_t parent[NJ];
+  int8_t depth[NJ];
+  int max_depth;
+};
+
+struct hp3d_smpl {
+  float* v_template = nullptr;   // [VPITCH]
+  float* shapedirs_t = nullptr;  // [10][VPITCH]
+  float* posedirs = nullptr;     // [207][VPITCH]
+  float* J_template = nullptr;   // [72]
+  float* J_shapedirs = nullptr;  // [72][10]
+  int skin_k = 0;
+  uint8_t* skin_idx = nullptr;   // [skin_k][NV]
+  float* skin_w = nullptr;       // [skin_k][NV]
+  int* reg_rowptr = nullptr;     // [NREG+1]
+  int* reg_col = nullptr;
+  float* reg_val = nullptr;
+  int* pick_ids = nullptr;       // [NPICK]
+  SmplTree tree;
+  void* blend_tc = nullptr;      // tensor-core pose-blend operands (gemm_tc.cu), optional
+};
+
+// ------------------------------------------------------------------ shape blend (K=10, fp32 FFMA)
+// v_shaped[mb][c] = v_template[c] + sum_l beta[mb][l] * shapedirs[c][l];  J[mb] = J_t + J_s beta.
+__global__ void __launch_bounds__(256) shape_blend_kernel(const float* __restrict__ betas, int Mb,
+                                                          const float* __restrict__ v_template,
+                                                          const float* __restrict__ shapedirs_t,
+                                                          const float* __restrict__ J_template,
+                                                          const float* __restrict__ J_shapedirs,
+                                                          float* __restrict__ v_shaped, float* __restrict__ J) {
+  const int mb = blockIdx.y;
+  __shared__ float sb[NBETA];
+  if (threadIdx.x < NBETA) sb[threadIdx.x] = betas[mb * NBETA + threadIdx.x];
+  __syncthreads();
+  const int c4 = blockIdx.x * blockDim.x + threadIdx.x;   // float4 index within the padded row
+  if (c4 < VPITCH / 4) {
+    float4 acc = reinterpret_cast<const float4*>(v_template)[c4];
+#pragma unroll
+    for (int l = 0; l < NBETA; ++l) {
+      const float4 s = reinterpret_cast<const float4*>(shapedirs_t + (size_t)l * VPITCH)[c4];
+      const float b = sb[l];
+      acc.x = fmaf(b, s.x, acc.x); acc.y = fmaf(b, s.y, acc.y); acc.z = fmaf(b, s.z, acc.z); acc.w = fmaf(b, s.w, acc.w);
+    }
+    reinterpret_cast<float4*>(v_shaped + (size_t)mb * VPITCH)[c4] = acc;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < NJ * 3) {
+    float a = J_template[threadIdx.x];
+#pragma unroll
+    for (int l = 0; l < NBETA; ++l) a = fmaf(sb[l], J_shapedirs[threadIdx.x * NBETA + l], a);
+    J[(size_t)mb * NJ * 3 + threadIdx.x] = a;
+  }
+}
+
+// ------------------------------------------------------------------ pose blend, fp32 CUDA-core GEMM
+// v_posed[m][c] = v_shaped[m/rep][c] + sum_k (R[m][k] - I[k]) * posedirs[k][c],  K = 207.
+// Exact-fp32 variant (parity path). The tensor-core variant lives in gemm_tc.cu.
+constexpr int PB_BM = 128, PB_BN = 128, PB_BK = 8;
+__global__ void __launch_bounds__(256) pose_blend_fp32_kernel(const float* __restrict__ body_pose,
+                                                              const float* __restrict__ posedirs,
+                                                              const float* __restrict__ v_shaped, int M, int rep,
+                                                              float* __restrict__ v_posed) {
+  __shared__ float As[PB_BK][PB_BM + 4];
+  __shared__ __align__(16) float Bs[PB_BK][PB_BN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * PB_BM, n0 = blockIdx.x * PB_BN;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < NPF; k0 += PB_BK) {
+    // A tile: 128 meshes x 8 features, pose feature computed on the fly
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = (tid >> 3) + 32 * i, k = k0 + (tid & 7), m = m0 + r;
+      float v = 0.f;
+      if (m < M && k < NPF) {
+        const int e = k % 9;
+        v = body_pose[(size_t)m * NPF + k] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+      }
+      As[tid & 7][r] = v;
+    }
+    {
+      const int r = tid >> 5, c4 = tid & 31, k = k0 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < NPF) v = *reinterpret_cast<const float4*>(posedirs + (size_t)k * VPITCH + n0 + c4 * 4);
+      *reinterpret_cast<float4*>(&Bs[r][c4 * 4]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < PB_BK; ++kk) {
+      float a[8], b[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; a[4 + i] = As[kk][64 + ty * 4 + i]; }
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[kk][64 + tx * 4]);
+      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+    const float* vs = v_shaped + (size_t)(m / rep) * VPITCH;
+    float* out = v_posed + (size_t)m * NV3;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int n = n0 + h * 64 + tx * 4;
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int nn = n + 2 * p;
+        if (nn < NV3) {
+          float2 o;
+          o.x = vs[nn] + acc[i][h * 4 + 2 * p];
+          o.y = vs[nn + 1] + acc[i][h * 4 + 2 * p + 1];
+          *reinterpret_cast<float2*>(out + nn) = o;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ fused FK + LBS + joints
+// One CTA per mesh (grid-stride). Warp 0 walks the 24-joint tree level by level in shared memory
+// (G_j = G_parent * [R_j | J_j - J_parent]), forms A_j = [R^G_j | t^G_j - R^G_j J_j], then all
+// threads skin the 6890 vertices: v' = (sum_k w_k A_{idx_k}) [v;1]. Epilogue: 24 posed joints,
+// 21 picked vertices, 45 sparse-regressed joints (read back through L2).
+__device__ __forceinline__ void mat3_mul(const float* a, const float* b, float* c) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      c[i * 3 + j] = fmaf(a[i * 3 + 2], b[6 + j], fmaf(a[i * 3 + 1], b[3 + j], a[i * 3] * b[j]));
+}
+
+__global__ void __launch_bounds__(256) lbs_kernel(const float* __restrict__ v_posed, const float* __restrict__ J,
+                                                  int Mb, const float* __restrict__ global_orient, int Mg,
+                                                  const float* __restrict__ body_pose, int M,
+                                                  const uint8_t* __restrict__ skin_idx,
+                                                  const float* __restrict__ skin_w, int skin_k,
+                                                  const int* __restrict__ reg_rowptr, const int* __restrict__ reg_col,
+                                                  const float* __restrict__ reg_val, const int* __restrict__ pick_ids,
+                                                  SmplTree tree, float* __restrict__ vertices,
+                                                  float* __restrict__ joints) {
+  __shared__ float4 sA[NJ][3];
+  __shared__ float sG[NJ][12];
+  const int tid = threadIdx.x;
+  const int repb = M / Mb, repg = M / Mg;
+  for (int m = blockIdx.x; m < M; m += gridDim.x) {
+    if (tid < 32) {
+      const int j = tid;
+      float R[9], Jj[3] = {0.f, 0.f, 0.f}, rel[3] = {0.f, 0.f, 0.f};
+      int par = -1, dep = 99;
+      if (j < NJ) {
+        const float* src = (j == 0) ? (global_orient + (size_t)(m / repg) * 9)
+                                    : (body_pose + ((size_t)m * NBJ + (j - 1)) * 9);
+#pragma unroll
+        for (int e = 0; e < 9; ++e) R[e] = src[e];
+        const float* Jm = J + (size_t)(m / repb) * NJ * 3;
+        par = tree.parent[j]; dep = tree.depth[j];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) { Jj[e] = Jm[j * 3 + e]; rel[e] = (par >= 0) ? (Jj[e] - Jm[par * 3 + e]) : Jj[e]; }
+      }
+      float G[12];
+      for (int d = 0; d <= tree.max_depth; ++d) {
+        if (dep == d) {
+          if (par < 0) {
+#pragma unroll
+            for (int e = 0; e < 9; ++e) G[e] = R[e];
+            G[9] = rel[0]; G[10] = rel[1]; G[11] = rel[2];
+          } else {
+            float P[12];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) P[e] = sG[par][e];
+            mat3_mul(P, R, G);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+              G[9 + i] = fmaf(P[i * 3 + 2], rel[2], fmaf(P[i * 3 + 1], rel[1], P[i * 3] * rel[0])) + P[9 + i];
+          }
+#pragma unroll
+          for (int e = 0; e < 12; ++e) sG[j][e] = G[e];
+        }
+        __syncwarp();
+      }
+      if (j < NJ) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float t = G[9 + i] - fmaf(G[i * 3 + 2], Jj[2], fmaf(G[i * 3 + 1], Jj[1], G[i * 3] * Jj[0]));
+          sA[j][i] = make_float4(G[i * 3], G[i * 3 + 1], G[i * 3 + 2], t);
+        }
+        if (joints) {
+          float* jo = joints + ((size_t)m * NOUTJ + j) * 3;
+          jo[0] = G[9]; jo[1] = G[10]; jo[2] = G[11];
+        }
+      }
+    }
+    __syncthreads();
+    const float* vp = v_posed + (size_t)m * NV3;
+    float* vo = vertices + (size_t)m * NV3;
+    for (int v = tid; v < NV; v += blockDim.x) {
+      const float x = vp[3 * v], y = vp[3 * v + 1], z = vp[3 * v + 2];
+      float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0, t2 = t0;
+      for (int k = 0; k < skin_k; ++k) {
+        const int j = skin_idx[k * NV + v];
+        const float w = skin_w[k * NV + v];
+        const float4 a0 = sA[j][0], a1 = sA[j][1], a2 = sA[j][2];
+        t0.x = fmaf(w, a0.x, t0.x); t0.y = fmaf(w, a0.y, t0.y); t0.z = fmaf(w, a0.z, t0.z); t0.w = fmaf(w, a0.w, t0.w);
+        t1.x = fmaf(w, a1.x, t1.x); t1.y = fmaf(w, a1.y, t1.y); t1.z = fmaf(w, a1.z, t1.z); t1.w = fmaf(w, a1.w, t1.w);
+        t2.x = fmaf(w, a2.x, t2.x); t2.y = fmaf(w, a2.y, t2.y); t2.z = fmaf(w, a2.z, t2.z); t2.w = fmaf(w, a2.w, t2.w);
+      }
+      vo[3 * v]     = fmaf(t0.z, z, fmaf(t0.y, y, t0.x * x)) + t0.w;
+      vo[3 * v + 1] = fmaf(t1.z, z, fmaf(t1.y, y, t1.x * x)) + t1.w;
+      vo[3 * v + 2] = fmaf(t2.z, z, fmaf(t2.y, y, t2.x * x)) + t2.w;
+    }
+    __syncthreads();   // vertices of this mesh visible to the whole CTA; sA reusable
+    if (joints && tid < NPICK + NREG) {
+      float ax = 0.f, ay = 0.f, az = 0.f;
+      if (tid < NPICK) {
+        const int v = pick_ids[tid];
+        ax = __ldcg(vo + 3 * v); ay = __ldcg(vo + 3 * v + 1); az = __ldcg(vo + 3 * v + 2);
+      } else {
+        const int r = tid - NPICK;
+        for (int p = reg_rowptr[r]; p < reg_rowptr[r + 1]; ++p) {
+          const int v = reg_col[p];
+          const float w = reg_val[p];
+          ax = fmaf(w, __ldcg(vo + 3 * v), ax); ay = fmaf(w, __ldcg(vo + 3 * v + 1), ay); az = fmaf(w, __ldcg(vo + 3 * v + 2), az);
+        }
+      }
+      float* jo = joints + ((size_t)m * NOUTJ + NJ + tid) * 3;
+      jo[0] = ax; jo[1] = ay; jo[2] = az;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ small rotation kernels
+__global__ void rodrigues_kernel(const float* __restrict__ aa, int n, float* __restrict__ R) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // smplx batch_rodrigues: angle = ||r + 1e-8||, dir = r / angle, R = I + sin K + (1 - cos) K^2
+  const float rx = aa[3 * i], ry = aa[3 * i + 1], rz = aa[3 * i + 2];
+  const float ex = rx + 1e-8f, ey = ry + 1e-8f, ez = rz + 1e-8f;
+  const float angle = sqrtf(ex * ex + ey * ey + ez * ez);
+  const float dx = rx / angle, dy = ry / angle, dz = rz / angle;
+  float s, c;
+  sincosf(angle, &s, &c);
+  const float oc = 1.f - c;
+  // K = [[0,-dz,dy],[dz,0,-dx],[-dy,dx,0]];  K^2 = d d^T - |d|^2 I
+  const float dd = dx * dx + dy * dy + dz * dz;
+  float* o = R + 9 * (size_t)i;
+  o[0] = 1.f + oc * (dx * dx - dd); o[1] = -s * dz + oc * dx * dy;    o[2] = s * dy + oc * dx * dz;
+  o[3] = s * dz + oc * dx * dy;     o[4] = 1.f + oc * (dy * dy - dd); o[5] = -s * dx + oc * dy * dz;
+  o[6] = -s * dy + oc * dx * dz;    o[7] = s * dx + oc * dy * dz;     o[8] = 1.f + oc * (dz * dz - dd);
+}
+
+__global__ void rot6d_kernel(const float* __restrict__ x, int n, float* __restrict__ R) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // reference utils/rigid_transform_utils.py:88-94: x.view(-1,3,2): a1 = elements 0,2,4; a2 = 1,3,5;
+  // F.normalize uses max(||a||, 1e-12); columns stacked (b1,b2,b3).
+  const float* p = x + 6 * (size_t)i;
+  float a1[3] = {p[0], p[2], p[4]}, a2[3] = {p[1], p[3], p[5]};
+  float n1 = fmaxf(sqrtf(a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2]), 1e-12f);
+  float b1[3] = {a1[0] / n1, a1[1] / n1, a1[2] / n1};
+  const float d = b1[0] * a2[0] + b1[1] * a2[1] + b1[2] * a2[2];
+  float u[3] = {a2[0] - d * b1[0], a2[1] - d * b1[1], a2[2] - d * b1[2]};
+  float n2 = fmaxf(sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]), 1e-12f);
+  float b2[3] = {u[0] / n2, u[1] / n2, u[2] / n2};
+  float b3[3] = {b1[1] * b2[2] - b1[2] * b2[1], b1[2] * b2[0] - b1[0] * b2[2], b1[0] * b2[1] - b1[1] * b2[0]};
+  float* o = R + 9 * (size_t)i;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) { o[r * 3] = b1[r]; o[r * 3 + 1] = b2[r]; o[r * 3 + 2] = b3[r]; }
+}
+
+// ------------------------------------------------------------------ per-vertex sample statistics
+// reference utils/sampling_utils.py:189-190, batched over images: thread = (image, vertex).
+__global__ void __launch_bounds__(256) vertex_uncertainty_kernel(const float* __restrict__ verts, int B, int N,
+                                                                 float* __restrict__ mean_out,
+                                                                 float* __restrict__ dist_out) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (v >= NV) return;
+  const float* base = verts + ((size_t)b * N) * NV3 + 3 * v;
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float* p = base + (size_t)n * NV3;
+    sx += p[0]; sy += p[1]; sz += p[2];
+  }
+  const float inv = 1.f / (float)N;
+  const float mx = sx * inv, my = sy * inv, mz = sz * inv;
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float* p = base + (size_t)n * NV3;
+    const float dx = p[0] - mx, dy = p[1] - my, dz = p[2] - mz;
+    acc += sqrtf(dx * dx + dy * dy + dz * dz);
+  }
+  dist_out[(size_t)b * NV + v] = acc * inv;
+  if (mean_out) {
+    float* mo = mean_out + ((size_t)b * NV + v) * 3;
+    mo[0] = mx; mo[1] = my; mo[2] = mz;
+  }
+}
+
+// ------------------------------------------------------------------ host side
+namespace hp3d {
+int blend_tc_create(const double* posedirs, void** out);                      // gemm_tc.cu
+void blend_tc_destroy(void* p);
+int blend_tc_forward(void* p, const float* v_shaped, int Mb, const float* body_pose, int M, float* v_posed,
+                     cudaStream_t stream);
+}
+
+extern "C" int hp3d_smpl_create(const hp3d_smpl_model* md, hp3d_smpl** out) {
+  HP3D_ARG(md && out, "null argument");
+  HP3D_ARG(md->v_template && md->shapedirs && md->posedirs && md->J_regressor && md->lbs_weights && md->parents &&
+           md->extra_vertex_ids && md->joint_regressors_extra, "null model field");
+  hp3d_smpl* h = new hp3d_smpl();
+  int rc = 0;
+  // tree
+  HP3D_ARG(md->parents[0] < 0, "parents[0] must be -1");
+  h->tree.max_depth = 0;
+  for (int j = 0; j < NJ; ++j) {
+    const int p = md->parents[j];
+    if (j > 0 && (p < 0 || p >= j)) { delete h; set_error("hp3d_smpl_create: parents must satisfy 0 <= parents[j] < j"); return -1; }
+    h->tree.parent[j] = (int8_t)p;
+    h->tree.depth[j] = (j == 0) ? 0 : (int8_t)(h->tree.depth[p] + 1);
+    h->tree.max_depth = std::max<int>(h->tree.max_depth, h->tree.depth[j]);
+  }
+  std::vector<float> vt(VPITCH, 0.f), sd((size_t)NBETA * VPITCH, 0.f), pd((size_t)NPF * VPITCH, 0.f);
+  for (int c = 0; c < NV3; ++c) vt[c] = (float)md->v_template[c];
+  for (int c = 0; c < NV3; ++c)
+    for (int l = 0; l < NBETA; ++l) sd[(size_t)l * VPITCH + c] = (float)md->shapedirs[(size_t)c * NBETA + l];
+  for (int k = 0; k < NPF; ++k)
+    for (int c = 0; c < NV3; ++c) pd[(size_t)k * VPITCH + c] = (float)md->posedirs[(size_t)k * NV3 + c];
+  // J = J_regressor (v_template + shapedirs beta) is linear in beta: fold in fp64
+  std::vector<float> Jt(NJ * 3), Js((size_t)NJ * 3 * NBETA);
+  for (int j = 0; j < NJ; ++j)
+    for (int e = 0; e < 3; ++e) {
+      double a = 0.0, s[NBETA] = {0};
+      for (int v = 0; v < NV; ++v) {
+        const double w = md->J_regressor[(size_t)j * NV + v];
+        if (w == 0.0) continue;
+        a += w * md->v_template[v * 3 + e];
+        for (int l = 0; l < NBETA; ++l) s[l] += w * md->shapedirs[((size_t)v * 3 + e) * NBETA + l];
+      }
+      Jt[j * 3 + e] = (float)a;
+      for (int l = 0; l < NBETA; ++l) Js[(size_t)(j * 3 + e) * NBETA + l] = (float)s[l];
+    }
+  // skinning weights: per-vertex non-zeros, padded to the max count
+  int K = 1;
+  for (int v = 0; v < NV; ++v) {
+    int c = 0;
+    for (int j = 0; j < NJ; ++j) c += md->lbs_weights[(size_t)v * NJ + j] != 0.0;
+    K = std::max(K, c);
+  }
+  std::vector<uint8_t> sidx((size_t)K * NV, 0);
+  std::vector<float> sw((size_t)K * NV, 0.f);
+  for (int v = 0; v < NV; ++v) {
+    int c = 0;
+    for (int j = 0; j < NJ; ++j) {
+      const double w = md->lbs_weights[(size_t)v * NJ + j];
+      if (w != 0.0) { sidx[(size_t)c * NV + v] = (uint8_t)j; sw[(size_t)c * NV + v] = (float)w; ++c; }
+    }
+    for (; c < K; ++c) sidx[(size_t)c * NV + v] = sidx[v];   // zero weight, benign index
+  }
+  h->skin_k = K;
+  std::vector<int> rp(NREG + 1, 0), rcol;
+  std::vector<float> rval;
+  for (int r = 0; r < NREG; ++r) {
+    for (int v = 0; v < NV; ++v) {
+      const double w = md->joint_regressors_extra[(size_t)r * NV + v];
+      if (w != 0.0) { rcol.push_back(v); rval.push_back((float)w); }
+    }
+    rp[r + 1] = (int)rcol.size();
+  }
+  if (rcol.empty()) { rcol.push_back(0); rval.push_back(0.f); }
+  std::vector<int> picks(md->extra_vertex_ids, md->extra_vertex_ids + NPICK);
+  for (int p : picks) if (p < 0 || p >= NV) { delete h; set_error("hp3d_smpl_create: extra_vertex_ids out of range"); return -1; }
+  rc = rc ? rc : upload(&h->v_template, vt.data(), vt.size());
+  rc = rc ? rc : upload(&h->shapedirs_t, sd.data(), sd.size());
+  rc = rc ? rc : upload(&h->posedirs, pd.data(), pd.size());
+  rc = rc ? rc : upload(&h->J_template, Jt.data(), Jt.size());
+  rc = rc ? rc : upload(&h->J_shapedirs, Js.data(), Js.size());
+  rc = rc ? rc : upload(&h->skin_idx, sidx.data(), sidx.size());
+  rc = rc ? rc : upload(&h->skin_w, sw.data(), sw.size());
+  rc = rc ? rc : upload(&h->reg_rowptr, rp.data(), rp.size());
+  rc = rc ? rc : upload(&h->reg_col, rcol.data(), rcol.size());
+  rc = rc ? rc : upload(&h->reg_val, rval.data(), rval.size());
+  rc = rc ? rc : upload(&h->pick_ids, picks.data(), picks.size());
+  rc = rc ? rc : blend_tc_create(md->posedirs, &h->blend_tc);
+  if (rc) { hp3d_smpl_destroy(h); return rc; }
+  *out = h;
+  return 0;
+}
+
+extern "C" void hp3d_smpl_destroy(hp3d_smpl* h) {
+  if (!h) return;
+  cudaFree(h->v_template); cudaFree(h->shapedirs_t); cudaFree(h->posedirs); cudaFree(h->J_template);
+  cudaFree(h->J_shapedirs); cudaFree(h->skin_idx); cudaFree(h->skin_w); cudaFree(h->reg_rowptr);
+  cudaFree(h->reg_col); cudaFree(h->reg_val); cudaFree(h->pick_ids);
+  blend_tc_destroy(h->blend_tc);
+  delete h;
+}
+
+static size_t ws_vshaped(int Mb) { return align_up((size_t)Mb * VPITCH * sizeof(float), 256); }
+static size_t ws_J(int Mb) { return align_up((size_t)Mb * NJ * 3 * sizeof(float), 256); }
+static size_t ws_vposed(int M) { return align_up((size_t)M * NV3 * sizeof(float), 256); }
+
+extern "C" size_t hp3d_smpl_workspace_bytes(const hp3d_smpl*, int M, int Mb) {
+  if (M <= 0 || Mb <= 0) return 0;
+  return ws_vshaped(Mb) + ws_J(Mb) + ws_vposed(M);
+}
+
+extern "C" int hp3d_smpl_shape_blend(const hp3d_smpl* h, const float* betas, int Mb, float* v_shaped, float* J,
+                                     void* stream) {
+  HP3D_ARG(h && betas && v_shaped && J && Mb > 0, "bad argument");
+  dim3 grid(cdiv(VPITCH / 4, 256), Mb);
+  shape_blend_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(betas, Mb, h->v_template, h->shapedirs_t, h->J_template,
+                                                              h->J_shapedirs, v_shaped, J);
+  return launch_status("shape_blend_kernel");
+}
+
+static int g_blend_mode = -1;   // -1 unset; 0 fp32 CUDA-core; 1 tensor-core
+static int blend_mode() {
+  if (g_blend_mode < 0) {
+    const char* e = getenv("HP3D_BLEND");
+    g_blend_mode = (e && !strcmp(e, "fp32")) ? 0 : 1;
+  }
+  return g_blend_mode;
+}
+
+extern "C" int hp3d_smpl_pose_blend(const hp3d_smpl* h, const float* v_shaped, int Mb, const float* body_pose, int M,
+                                    float* v_posed, void* stream) {
+  HP3D_ARG(h && v_shaped && body_pose && v_posed && M > 0 && Mb > 0 && M % Mb == 0, "bad argument");
+  if (blend_mode() == 1 && h->blend_tc)
+    return blend_tc_forward(h->blend_tc, v_shaped, Mb, body_pose, M, v_posed, (cudaStream_t)stream);
+  dim3 grid(cdiv(NV3, PB_BN), cdiv(M, PB_BM));
+  pose_blend_fp32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(body_pose, h->posedirs, v_shaped, M, M / Mb, v_posed);
+  return launch_status("pose_blend_fp32_kernel");
+}
+
+extern "C" int hp3d_smpl_lbs(const hp3d_smpl* h, const float* v_posed, const float* J, int Mb,
+                             const float* global_orient, int Mg, const float* body_pose, int M, float* vertices,
+                             float* joints, void* stream) {
+  HP3D_ARG(h && v_posed && J && global_orient && body_pose && vertices, "null argument");
+  HP3D_ARG(M > 0 && Mb > 0 && Mg > 0 && M % Mb == 0 && M % Mg == 0, "M must be a multiple of Mb and Mg");
+  const int grid = std::min(M, 148 * 8);
+  lbs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M, h->skin_idx,
+                                                      h->skin_w, h->skin_k, h->reg_rowptr, h->reg_col, h->reg_val,
+                                                      h->pick_ids, h->tree, vertices, joints);
+  return launch_status("lbs_kernel");
+}
+
+extern "C" int hp3d_smpl_forward(const hp3d_smpl* h, const float* betas, int Mb, const float* global_orient, int Mg,
+                                 const float* body_pose, int M, float* vertices, float* joints, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  HP3D_ARG(h && betas && global_orient && body_pose && vertices && workspace, "null argument");
+  HP3D_ARG(M > 0 && Mb > 0 && Mg > 0 && M % Mb == 0 && M % Mg == 0, "M must be a multiple of Mb and Mg");
+  HP3D_ARG(workspace_bytes >= hp3d_smpl_workspace_bytes(h, M, Mb), "workspace too small");
+  char* ws = (char*)workspace;
+  float* v_shaped = (float*)ws; ws += ws_vshaped(Mb);
+  float* J = (float*)ws; ws += ws_J(Mb);
+  float* v_posed = (float*)ws;
+  int rc = hp3d_smpl_shape_blend(h, betas, Mb, v_shaped, J, stream);
+  if (rc) return rc;
+  rc = hp3d_smpl_pose_blend(h, v_shaped, Mb, body_pose, M, v_posed, stream);
+  if (rc) return rc;
+  return hp3d_smpl_lbs(h, v_posed, J, Mb, global_orient, Mg, body_pose, M, vertices, joints, stream);
+}
+
+extern "C" int hp3d_rodrigues(const float* aa, int n, float* R, void* stream) {
+  HP3D_ARG(aa && R && n > 0, "bad argument");
+  rodrigues_kernel<<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(aa, n, R);
+  return launch_status("rodrigues_kernel");
+}
+
+extern "C" int hp3d_rot6d_to_rotmat(const float* x, int n, float* R, void* stream) {
+  HP3D_ARG(x && R && n > 0, "bad argument");
+  rot6d_kernel<<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>(x, n, R);
+  return launch_status("rot6d_kernel");
+}
+
+extern "C" int hp3d_vertex_uncertainty(const float* vertices, int B, int N, float* mean_vertices, float* avg_dist,
+                                       void* stream) {
+  HP3D_ARG(vertices && avg_dist && B > 0 && N > 0, "bad argument");
+  dim3 grid(cdiv(NV, 256), B);
+  vertex_uncertainty_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(vertices, B, N, mean_vertices, avg_dist);
+  return launch_status("vertex_uncertainty_kernel");
+}

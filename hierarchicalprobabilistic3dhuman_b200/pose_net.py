@@ -1,0 +1,202 @@
+"""Drop-in for the reference's `models.poseMF_shapeGaussian_net.PoseMFShapeGaussianNet`
+(reference models/poseMF_shapeGaussian_net.py:24-162; constructed at run_predict.py:68-71).
+
+Same constructor `(smpl_parents, config)`, same parameter/buffer names and shapes (so
+`load_state_dict(checkpoint['best_model_state_dict'])` works unchanged), same
+`forward(input, input_feats=None)` 8-tuple. The torch modules below only hold parameters; all
+arithmetic runs in libhp3d (ResNet-18 encoder kernels + hierarchical matrix-Fisher head kernels)."""
+import ctypes
+import os
+
+import numpy as np
+import torch
+from torch import nn
+from torch.distributions import Normal
+
+from . import _lib
+from .synthetic import ancestors_from_parents
+
+ENC_MODES = {"parity": 0, "fast": 1}
+
+
+class _Block(nn.Module):
+    def __init__(self, inplanes, planes, stride):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = None
+        if stride != 1 or inplanes != planes:
+            self.downsample = nn.Sequential(nn.Conv2d(inplanes, planes, 1, stride, bias=False), nn.BatchNorm2d(planes))
+
+
+class _ResNet18Params(nn.Module):
+    """Parameter container with torchvision/reference naming (reference models/resnet.py:146-157)."""
+
+    def __init__(self, in_channels):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_channels, 64, 7, 2, 3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        inpl = 64
+        for li, planes in enumerate((64, 128, 256, 512), start=1):
+            stride = 1 if li == 1 else 2
+            setattr(self, f"layer{li}", nn.Sequential(_Block(inpl, planes, stride), _Block(planes, planes, 1)))
+            inpl = planes
+        for m in self.modules():   # same initialisation as the reference (:161-166)
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+
+class PoseMFShapeGaussianNet(nn.Module):
+    def __init__(self, smpl_parents, config, encoder_mode=None):
+        super().__init__()
+        self.config = config
+        if config.MODEL.NUM_RESNET_LAYERS != 18:
+            raise NotImplementedError("libhp3d implements the ResNet-18 encoder (reference default NUM_RESNET_LAYERS=18)")
+        if config.MODEL.NUM_IN_CHANNELS != 18 or config.MODEL.EMBED_DIM != 256 or config.MODEL.NUM_SMPL_BETAS != 10:
+            raise NotImplementedError("libhp3d is specialised to NUM_IN_CHANNELS=18, EMBED_DIM=256, NUM_SMPL_BETAS=10")
+        self.smpl_parents = [int(p) for p in smpl_parents]
+        self.parents_dict = ancestors_from_parents(self.smpl_parents)
+        self.num_joints = len(self.parents_dict)
+        self.num_shape_params = 10
+        self.num_glob_params = 6
+        self.num_cam_params = 3
+        self.encoder_mode = encoder_mode or os.environ.get("HP3D_ENCODER_MODE", "fast")
+        assert self.encoder_mode in ENC_MODES
+        self.register_buffer("init_glob", torch.tensor([[1., 0., 0., 1., 0., 0.]]))   # rotmat_to_rot6d(I), :45
+        self.register_buffer("init_cam", torch.tensor([0.9, 0.0, 0.0]))
+        self.image_encoder = _ResNet18Params(18)
+        self.activation = nn.ELU()
+        self.fc1 = nn.Linear(512, 512)
+        self.fc_shape = nn.Linear(512, 20)
+        self.fc_glob = nn.Linear(512, 6)
+        self.fc_cam = nn.Linear(512, 3)
+        self.fc_embed = nn.Linear(512 + 20 + 6 + 3, 256)
+        self.fc_pose = nn.ModuleList()
+        for j in range(self.num_joints):
+            self.fc_pose.append(nn.Sequential(nn.Linear(256 + 21 * len(self.parents_dict[j]), 128), self.activation,
+                                              nn.Linear(128, 9)))
+        self._handles = {}
+        self._ws = _lib.Workspace()
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._drop_handles())
+
+    # ------------------------------------------------------------------ handles
+    def _drop_handles(self):
+        try:
+            L = _lib.lib()
+        except RuntimeError:
+            self._handles = {}
+            return
+        for enc, head in self._handles.values():
+            if enc: L.hp3d_encoder_destroy(enc)
+            if head: L.hp3d_head_destroy(head)
+        self._handles = {}
+
+    def __del__(self):
+        try:
+            self._drop_handles()
+        except Exception:
+            pass
+
+    def refresh_weights(self):
+        """Call after mutating parameters in place (handles hold repacked copies)."""
+        self._drop_handles()
+
+    def _build_handles(self, key, need_encoder):
+        L = _lib.lib()
+        enc, head = self._handles.get(key, (None, None))
+        keep = []
+        c = lambda t: (keep.append(np.ascontiguousarray(t.detach().cpu().numpy().astype(np.float32))) or keep[-1].ctypes.data_as(ctypes.c_void_p))
+        with torch.cuda.device(key):
+            if head is None:
+                hw = _lib.HeadWeights()
+                for n in ("fc1", "fc_shape", "fc_glob", "fc_cam", "fc_embed"):
+                    setattr(hw, n + "_w", c(getattr(self, n).weight)); setattr(hw, n + "_b", c(getattr(self, n).bias))
+                arr = lambda items: (ctypes.c_void_p * 23)(*[ctypes.cast(x, ctypes.c_void_p).value for x in items])
+                a0w = arr([c(self.fc_pose[j][0].weight) for j in range(23)]); a0b = arr([c(self.fc_pose[j][0].bias) for j in range(23)])
+                a2w = arr([c(self.fc_pose[j][2].weight) for j in range(23)]); a2b = arr([c(self.fc_pose[j][2].bias) for j in range(23)])
+                keep += [a0w, a0b, a2w, a2b]
+                hw.fc_pose0_w, hw.fc_pose0_b, hw.fc_pose2_w, hw.fc_pose2_b = a0w, a0b, a2w, a2b
+                hw.init_glob = c(self.init_glob); hw.init_cam = c(self.init_cam)
+                par = np.ascontiguousarray(self.smpl_parents, np.int32); keep.append(par)
+                hw.parents = par.ctypes.data_as(ctypes.c_void_p)
+                hw.delta_i_weight = float(self.config.MODEL.DELTA_I_WEIGHT) if self.config.MODEL.DELTA_I else 0.0
+                out = ctypes.c_void_p()
+                _lib.check(L.hp3d_head_create(ctypes.byref(hw), ctypes.byref(out)), "hp3d_head_create")
+                head = out
+            if need_encoder and enc is None:
+                ew = _lib.EncoderWeights()
+
+                def fill(cb, conv, bn):
+                    cb.w = c(conv.weight); cb.cout, cb.cin = conv.out_channels, conv.in_channels
+                    cb.k, cb.stride, cb.pad = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+                    cb.bn_w, cb.bn_b, cb.bn_mean, cb.bn_var = c(bn.weight), c(bn.bias), c(bn.running_mean), c(bn.running_var)
+                e = self.image_encoder
+                fill(ew.stem, e.conv1, e.bn1)
+                for li in range(4):
+                    layer = getattr(e, f"layer{li + 1}")
+                    for bi in range(2):
+                        blk = layer[bi]
+                        fill(ew.conv[li][bi][0], blk.conv1, blk.bn1)
+                        fill(ew.conv[li][bi][1], blk.conv2, blk.bn2)
+                    if layer[0].downsample is not None:
+                        fill(ew.down[li], layer[0].downsample[0], layer[0].downsample[1])
+                ew.bn_eps = float(e.bn1.eps)
+                out = ctypes.c_void_p()
+                _lib.check(L.hp3d_encoder_create(ctypes.byref(ew), ENC_MODES[self.encoder_mode], ctypes.byref(out)),
+                           "hp3d_encoder_create")
+                enc = out
+        self._handles[key] = (enc, head)
+        return enc, head
+
+    # ------------------------------------------------------------------ stages
+    def encode(self, input):
+        """(B,18,H,W) fp32 NCHW on CUDA -> (B,512) features (reference models/resnet.py:202-217)."""
+        _lib.require_cuda(input, "input")
+        dev = input.device
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        enc, _ = self._build_handles(key, True)
+        x = input.detach().to(torch.float32).contiguous()
+        B, C, H, W = x.shape
+        assert C == 18
+        L = _lib.lib()
+        feats = torch.empty(B, 512, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            nbytes = L.hp3d_encoder_workspace_bytes(enc, B, H, W)
+            ws = self._ws.get(nbytes, dev)
+            _lib.check(L.hp3d_encoder_forward(enc, x.data_ptr(), B, H, W, feats.data_ptr(), ws.data_ptr(), ws.numel(),
+                                              _lib.stream_ptr()), "hp3d_encoder_forward")
+        return feats
+
+    def head(self, input_feats, teacher=None):
+        _lib.require_cuda(input_feats, "input_feats")
+        dev = input_feats.device
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        _, head = self._build_handles(key, False)
+        feats = input_feats.detach().to(torch.float32).contiguous()
+        B = feats.shape[0]
+        L = _lib.lib()
+        e = lambda *s: torch.empty(B, *s, device=dev, dtype=torch.float32)
+        F, U, S, V, mode = e(23, 3, 3), e(23, 3, 3), e(23, 3), e(23, 3, 3), e(23, 3, 3)
+        shape_params, glob, cam = e(20), e(6), e(3)
+        tp = [None, None, None]
+        if teacher is not None:
+            tp = [t.detach().to(device=dev, dtype=torch.float32).contiguous() for t in teacher]
+        with torch.cuda.device(dev):
+            nbytes = L.hp3d_head_workspace_bytes(head, B)
+            ws = self._ws.get(nbytes, dev)
+            _lib.check(L.hp3d_head_forward(head, feats.data_ptr(), B, F.data_ptr(), U.data_ptr(), S.data_ptr(),
+                                           V.data_ptr(), mode.data_ptr(), shape_params.data_ptr(), glob.data_ptr(),
+                                           cam.data_ptr(), *[t.data_ptr() if t is not None else None for t in tp],
+                                           ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "hp3d_head_forward")
+        return F, U, S, V, mode, shape_params, glob, cam
+
+    def forward(self, input, input_feats=None):
+        """Returns (pose_F, pose_U, pose_S, pose_V, pose_rotmats_mode, shape_dist, glob, cam) exactly like the
+        reference (:162); pose_U / pose_V are the improper LAPACK-convention factors."""
+        if input_feats is None:
+            input_feats = self.encode(input)
+        F, U, S, V, mode, shape_params, glob, cam = self.head(input_feats)
+        shape_dist = Normal(loc=shape_params[:, :10], scale=torch.exp(shape_params[:, 10:]))
+        return F, U, S, V, mode, shape_dist, glob, cam

@@ -1,0 +1,103 @@
+"""Drop-ins for the reference's utils/sampling_utils.py on libhp3d kernels:
+`pose_matrix_fisher_sampling_torch` (:74-143) and
+`compute_vertex_uncertainties_by_poseMF_shapeGaussian_sampling` (:146-192), plus the batched
+(B images x N samples) composition the reference only spells out in its training loop
+(train/train_poseMF_shapeGaussian_net.py:293-308)."""
+import ctypes
+import torch
+
+from . import _lib
+
+_stats_buf = {}
+
+
+def _rng_seed_offset(device, n_rounds_bound):
+    """(seed, offset) from torch's per-device Philox generator, advancing it so successive calls
+    draw fresh streams (the reference consumes the global generator after torch.manual_seed)."""
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    seed = gen.initial_seed()
+    off = gen.get_offset()
+    gen.set_offset(off + 4 * ((2 * n_rounds_bound + 3) // 4))
+    return seed & 0xFFFFFFFFFFFFFFFF, off
+
+
+def pose_matrix_fisher_sampling_torch(pose_U, pose_S, pose_V, num_samples, b=1.5, oversampling_ratio=8,
+                                      sample_on_cpu=False, noise=None, return_stats=False, out=None):
+    """(B,J,3,3),(B,J,3),(B,J,3,3) -> (B,num_samples,J,3,3) rotation samples of M(U S V^T).
+    `sample_on_cpu` is accepted for signature compatibility and ignored (everything runs in one
+    kernel). `noise=(eps, w)` with eps (B,J,oversampling_ratio*N,4) standard normals and
+    w (B,J,oversampling_ratio*N) uniforms replays the reference's accept/compact rule exactly;
+    without it an in-kernel Philox stream seeded from torch's CUDA generator is used.
+    `out` may be a slice of a larger (e.g. all-gather) buffer."""
+    _lib.require_cuda(pose_U, "pose_U")
+    dev = pose_U.device
+    B, J = pose_U.shape[0], pose_U.shape[1]
+    f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+    U, S, V = f32(pose_U), f32(pose_S), f32(pose_V)
+    if out is None:
+        out = torch.empty(B, num_samples, J, 3, 3, device=dev, dtype=torch.float32)
+    else:
+        assert out.is_contiguous() and out.shape == (B, num_samples, J, 3, 3) and out.dtype == torch.float32
+    stats = torch.zeros(3, device=dev, dtype=torch.int64)
+    eps_p = w_p = None
+    seed = off = 0
+    if noise is not None:
+        eps, w = f32(noise[0]), f32(noise[1])
+        assert eps.shape == (B, J, oversampling_ratio * num_samples, 4) and w.shape == (B, J, oversampling_ratio * num_samples)
+        eps_p, w_p = eps.data_ptr(), w.data_ptr()
+    else:
+        seed, off = _rng_seed_offset(dev, 64 + 16 * ((num_samples + 31) // 32))
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().hp3d_mf_sample(U.data_ptr(), S.data_ptr(), V.data_ptr(), B, J, num_samples, float(b),
+                                             seed, off, eps_p, w_p, int(oversampling_ratio), out.data_ptr(),
+                                             stats.data_ptr(), _lib.stream_ptr()), "hp3d_mf_sample")
+    if return_stats:
+        return out, stats
+    return out
+
+
+def vertex_uncertainty(vertices):
+    """vertices (B,N,6890,3) -> (mean (B,6890,3), avg distance from the mean (B,6890));
+    reference utils/sampling_utils.py:189-190 batched over images."""
+    _lib.require_cuda(vertices, "vertices")
+    v = vertices.detach().to(torch.float32).contiguous()
+    B, N = v.shape[0], v.shape[1]
+    mean = torch.empty(B, 6890, 3, device=v.device, dtype=torch.float32)
+    dist = torch.empty(B, 6890, device=v.device, dtype=torch.float32)
+    with torch.cuda.device(v.device):
+        _lib.check(_lib.lib().hp3d_vertex_uncertainty(v.data_ptr(), B, N, mean.data_ptr(), dist.data_ptr(),
+                                                      _lib.stream_ptr()), "hp3d_vertex_uncertainty")
+    return mean, dist
+
+
+def compute_vertex_uncertainties_by_poseMF_shapeGaussian_sampling(pose_U, pose_S, pose_V, shape_distribution,
+                                                                  glob_rotmats, num_samples, smpl_model,
+                                                                  use_mean_shape=False):
+    """Reference signature and returns (utils/sampling_utils.py:146-192); batch size must be 1."""
+    assert pose_U.shape[0] == pose_S.shape[0] == pose_V.shape[0] == 1
+    R = pose_matrix_fisher_sampling_torch(pose_U, pose_S, pose_V, num_samples, b=1.5, oversampling_ratio=8)
+    if use_mean_shape:
+        betas = shape_distribution.loc                                  # (1,10): broadcast inside the kernel
+    else:
+        betas = shape_distribution.sample([num_samples])[:, 0, :]
+    out = smpl_model(body_pose=R[0], global_orient=glob_rotmats.unsqueeze(1), betas=betas, pose2rot=False)
+    _, dist = vertex_uncertainty(out.vertices[None])
+    return dist[0], out.vertices, out.joints
+
+
+def sample_meshes_batched(pose_U, pose_S, pose_V, shape_distribution, glob_rotmats, num_samples, smpl_model,
+                          use_mean_shape=True, noise=None, rotmats_out=None):
+    """B images x N samples in three launches (sampler, SMPL, statistics): returns dict with
+    rotmats (B,N,23,3,3), vertices (B,N,6890,3), joints (B,N,90,3), betas, per_vertex_uncertainty (B,6890)."""
+    B = pose_U.shape[0]
+    R = pose_matrix_fisher_sampling_torch(pose_U, pose_S, pose_V, num_samples, noise=noise, out=rotmats_out)
+    if use_mean_shape:
+        betas = shape_distribution.loc                                  # (B,10), each image's row reused N times
+    else:
+        betas = shape_distribution.sample([num_samples]).transpose(0, 1).reshape(B * num_samples, -1)
+    out = smpl_model(body_pose=R.view(B * num_samples, 23, 3, 3), global_orient=glob_rotmats.reshape(B, 1, 3, 3),
+                     betas=betas, pose2rot=False)
+    verts = out.vertices.view(B, num_samples, 6890, 3)
+    mean, dist = vertex_uncertainty(verts)
+    return dict(rotmats=R, vertices=verts, joints=out.joints.view(B, num_samples, 90, 3), betas=betas,
+                mean_vertices=mean, per_vertex_uncertainty=dist)

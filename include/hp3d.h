@@ -1,0 +1,140 @@
+/* libhp3d -- C ABI of the B200-native probabilistic-pose inference hot path.
+ *
+ * The reference (akashsengupta1997/HierarchicalProbabilistic3DHuman) is pure Python and has no FFI;
+ * the "interface" each entry point replaces is the Python call cited beside it (paths relative to
+ * the reference root). INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *  - every function returns int: 0 = OK, <0 = argument error, >0 = cudaError_t of the failing call;
+ *    hp3d_last_error() returns a thread-local message. Nothing throws or aborts.
+ *  - all tensor memory is caller-owned DEVICE memory (fp32, contiguous, 16-byte aligned base
+ *    pointers unless noted); model constants passed to *_create are HOST pointers and are copied /
+ *    repacked into an immutable opaque handle.
+ *  - kernels are enqueued on the given stream; no internal synchronisation, no global state.
+ *  - `stream` is a cudaStream_t passed as void* so the header needs no CUDA include.
+ */
+#ifndef HP3D_H_
+#define HP3D_H_
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HP3D_VERSION 100
+#define HP3D_NUM_VERTS 6890
+#define HP3D_NUM_JOINTS 24          /* SMPL skeleton incl. root */
+#define HP3D_NUM_BODY_JOINTS 23
+#define HP3D_NUM_BETAS 10
+#define HP3D_NUM_OUT_JOINTS 90      /* 24 posed + 21 picked + 45 regressed (models/smpl_official.py:30-34) */
+
+int hp3d_version(void);
+const char* hp3d_last_error(void);
+
+/* ---------------------------------------------------------------- SMPL forward
+ * replaces: models/smpl_official.py:13-41 (SMPL.__init__/forward) and, through it, smplx 0.1.26
+ * lbs() / vertices2joints() / batch_rigid_transform() / VertexJointSelector. */
+typedef struct hp3d_smpl hp3d_smpl;
+typedef struct {
+  const double* v_template;             /* [6890*3]                                   */
+  const double* shapedirs;              /* [6890*3*10]  (vertex, xyz, beta)           */
+  const double* posedirs;               /* [207 * 20670] (pose feature, vertex*3+xyz) */
+  const double* J_regressor;            /* [24*6890]                                  */
+  const double* lbs_weights;            /* [6890*24]                                  */
+  const int32_t* parents;               /* [24], parents[0] = -1                      */
+  const int32_t* extra_vertex_ids;      /* [21] vertices appended as joints 24..44    */
+  const double* joint_regressors_extra; /* [45*6890] rows appended as joints 45..89   */
+} hp3d_smpl_model;
+
+int hp3d_smpl_create(const hp3d_smpl_model* model, hp3d_smpl** out);
+void hp3d_smpl_destroy(hp3d_smpl* h);
+/* bytes of scratch hp3d_smpl_forward needs for M meshes with Mb distinct shapes */
+size_t hp3d_smpl_workspace_bytes(const hp3d_smpl* h, int M, int Mb);
+/* betas [Mb*10]; global_orient [Mg*9] row-major rotmats; body_pose [M*23*9]; M % Mb == 0 and
+ * M % Mg == 0: mesh m uses betas row m/(M/Mb) and global_orient row m/(M/Mg) (the reference's
+ * per-image expand over N samples, utils/sampling_utils.py:178-185, train/...:304-308).
+ * vertices [M*6890*3]; joints [M*90*3] (may be NULL). */
+int hp3d_smpl_forward(const hp3d_smpl* h, const float* betas, int Mb, const float* global_orient, int Mg,
+                      const float* body_pose, int M, float* vertices, float* joints,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* stage-level entry points (used by tests / profiling; hp3d_smpl_forward = these three in order) */
+int hp3d_smpl_shape_blend(const hp3d_smpl* h, const float* betas, int Mb, float* v_shaped /*[Mb*20672]*/,
+                          float* J /*[Mb*24*3]*/, void* stream);
+int hp3d_smpl_pose_blend(const hp3d_smpl* h, const float* v_shaped, int Mb, const float* body_pose, int M,
+                         float* v_posed /*[M*20670]*/, void* stream);
+int hp3d_smpl_lbs(const hp3d_smpl* h, const float* v_posed, const float* J, int Mb, const float* global_orient,
+                  int Mg, const float* body_pose, int M, float* vertices, float* joints, void* stream);
+/* smplx batch_rodrigues: axis-angle [n*3] -> rotmats [n*9] (pose2rot=True callers:
+ * evaluate/...:176-178, predict/...:136) */
+int hp3d_rodrigues(const float* axis_angle, int n, float* rotmats, void* stream);
+/* replaces utils/rigid_transform_utils.py:80-94 */
+int hp3d_rot6d_to_rotmat(const float* x6, int n, float* rotmats, void* stream);
+/* per-vertex sample statistics, replaces utils/sampling_utils.py:189-190 for B images x N samples:
+ * vertices [B*N*6890*3] -> mean_vertices [B*6890*3] (may be NULL), avg_dist [B*6890] */
+int hp3d_vertex_uncertainty(const float* vertices, int B, int N, float* mean_vertices, float* avg_dist, void* stream);
+
+/* ---------------------------------------------------------------- matrix-Fisher sampler
+ * replaces: utils/sampling_utils.py:74-143 (pose_matrix_fisher_sampling_torch) incl. :10-71
+ * (bingham_sampling_for_matrix_fisher_torch) and utils/rigid_transform_utils.py:113-133.
+ * U,V [B*J*9], S [B*J*3] (improper LAPACK factors as the head returns them); R_out [B*N*J*9].
+ * Noise: if eps/w are non-NULL (eps [B*J*ov*N*4] normals, w [B*J*ov*N] uniforms) the kernel replays
+ * the reference's "first N accepted of ov*N, in index order" rule exactly; otherwise Philox4x32-10
+ * keyed by (seed, offset) draws proposals until N are accepted (at most max_rounds*32 proposals).
+ * stats [3] (device, may be NULL): proposals, accepts, (image,joint) pairs that ran out of proposals. */
+int hp3d_mf_sample(const float* U, const float* S, const float* V, int B, int J, int N, float b,
+                   uint64_t seed, uint64_t offset, const float* eps, const float* w, int oversampling,
+                   float* R_out, unsigned long long* stats, void* stream);
+
+/* ---------------------------------------------------------------- distribution head
+ * replaces: models/poseMF_shapeGaussian_net.py:95-160 (everything after the encoder). */
+typedef struct hp3d_head hp3d_head;
+typedef struct {
+  const float *fc1_w, *fc1_b;           /* [512*512], [512]  (out, in) row-major like nn.Linear */
+  const float *fc_shape_w, *fc_shape_b; /* [20*512], [20]  */
+  const float *fc_glob_w, *fc_glob_b;   /* [6*512], [6]    */
+  const float *fc_cam_w, *fc_cam_b;     /* [3*512], [3]    */
+  const float *fc_embed_w, *fc_embed_b; /* [256*541], [256] */
+  const float* const* fc_pose0_w;       /* 23 pointers, [128*(256+21*n_anc[j])] */
+  const float* const* fc_pose0_b;       /* 23 pointers, [128] */
+  const float* const* fc_pose2_w;       /* 23 pointers, [9*128] */
+  const float* const* fc_pose2_b;       /* 23 pointers, [9] */
+  const float *init_glob, *init_cam;    /* [6], [3] */
+  const int32_t* parents;               /* [24] SMPL kinematic tree */
+  float delta_i_weight;                 /* MODEL.DELTA_I_WEIGHT (0 when MODEL.DELTA_I is False) */
+} hp3d_head_weights;
+int hp3d_head_create(const hp3d_head_weights* w, hp3d_head** out);
+void hp3d_head_destroy(hp3d_head* h);
+size_t hp3d_head_workspace_bytes(const hp3d_head* h, int B);
+/* feats [B*512] -> F,U,V,mode [B*23*9], S [B*23*3], shape_params [B*20] (mean | log_std),
+ * glob [B*6], cam [B*3]. teacher_* (may be NULL) teacher-force the ancestors' inputs (parity tests). */
+int hp3d_head_forward(const hp3d_head* h, const float* feats, int B, float* F, float* U, float* S, float* V,
+                      float* mode, float* shape_params, float* glob, float* cam,
+                      const float* teacher_Uproper, const float* teacher_Sproper, const float* teacher_mode,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- ResNet-18 encoder
+ * replaces: models/resnet.py:202-217 (ResNet.forward) for resnet18(in_channels=18), eval-mode BN. */
+typedef struct hp3d_encoder hp3d_encoder;
+typedef struct {
+  const float* w; int cout, cin, k, stride, pad;      /* conv weight [cout*cin*k*k] (OIHW) */
+  const float *bn_w, *bn_b, *bn_mean, *bn_var;        /* [cout] each */
+} hp3d_conv_bn;
+typedef struct {
+  hp3d_conv_bn stem;                    /* 7x7 s2 p3, 18->64 */
+  hp3d_conv_bn conv[4][2][2];           /* [layer][block][conv1|conv2] */
+  hp3d_conv_bn down[4];                 /* 1x1 s2 downsample of layers 2..4 (down[0] unused, w=NULL) */
+  float bn_eps;
+} hp3d_encoder_weights;
+#define HP3D_ENC_PARITY 0   /* fp32 CUDA-core implicit GEMM (<=1e-4 end-to-end contract)            */
+#define HP3D_ENC_FAST 1     /* fp16 operands, fp32 accumulate, tcgen05 tensor-core implicit GEMM   */
+int hp3d_encoder_create(const hp3d_encoder_weights* w, int mode, hp3d_encoder** out);
+void hp3d_encoder_destroy(hp3d_encoder* h);
+size_t hp3d_encoder_workspace_bytes(const hp3d_encoder* h, int B, int H, int W);
+/* x [B*18*H*W] fp32 NCHW (the reference's input layout, predict/...:100) -> feats [B*512] */
+int hp3d_encoder_forward(const hp3d_encoder* h, const float* x_nchw, int B, int H, int W, float* feats,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HP3D_H_ */

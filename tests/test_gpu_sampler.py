@@ -1,0 +1,93 @@
+"""CUDA matrix-Fisher sampler vs the reference's golden samples (injected-noise replay) and
+statistical checks for the in-kernel Philox mode."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import sampler_oracle
+from hierarchicalprobabilistic3dhuman_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["sampler_usv_b4_n8", "sampler_head_b4_n8", "sampler_lowk_b2_n100", "sampler_highk_b2_n100"])
+def test_injected_noise_reproduces_reference_samples(built_lib, name):
+    import hierarchicalprobabilistic3dhuman_b200 as hp
+    g = load_golden(name)
+    U, S, V = (torch.from_numpy(g[k]) for k in ("U", "S", "V"))
+    N = int(g["N"])
+    torch.manual_seed(int(g["seed"]))
+    eps, w = sampler_oracle.draw_noise(U.shape[0], U.shape[1], N)     # the reference's draw order
+    R, stats = hp.pose_matrix_fisher_sampling_torch(U.cuda(), S.cuda(), V.cuda(), N, noise=(eps.cuda(), w.cuda()), return_stats=True)
+    assert R.shape == (U.shape[0], N, 23, 3, 3)
+    assert int(stats[2]) == 0
+    # per (image, joint) comparison: an accept decision within 1 ulp of the threshold can shift one chain
+    d = (R.cpu().double() - torch.from_numpy(g["R"]).double()).abs().amax(dim=(1, 3, 4))     # (B, J)
+    bad = (d > 1e-4).sum().item()
+    assert bad == 0, f"{bad} of {d.numel()} (image,joint) chains differ"
+    assert rel_err(R, g["R"]) < 1e-4
+    Rc = R.cpu()
+    assert (torch.det(Rc) - 1).abs().max() < 1e-5
+    assert (Rc.transpose(-1, -2) @ Rc - torch.eye(3)).abs().max() < 1e-5
+
+
+def test_exhausted_proposals_are_reported(built_lib):
+    import hierarchicalprobabilistic3dhuman_b200 as hp
+    U, S, V = (torch.from_numpy(a) for a in syn.synthetic_usv(2, seed=5))
+    N = 8
+    eps = torch.randn(2, 23, N, 4); w = torch.ones(2, 23, N) * 2.0          # w >= 1: nothing is accepted
+    R, stats = hp.pose_matrix_fisher_sampling_torch(U.cuda(), S.cuda(), V.cuda(), N, oversampling_ratio=1,
+                                                    noise=(eps.cuda(), w.cuda()), return_stats=True)
+    assert int(stats[1]) == 0 and int(stats[2]) == 2 * 23
+    assert torch.isfinite(R).all()
+
+
+def _expected_rotation(S):
+    """E[R] = U diag(d log c / d s) V^T; the derivative by numerical integration of the MF normaliser
+    in quaternion form on a fine grid is overkill here -- use a large oracle Monte-Carlo run instead."""
+    raise NotImplementedError
+
+
+def test_philox_mode_statistics_match_oracle(built_lib):
+    import hierarchicalprobabilistic3dhuman_b200 as hp
+    # one image, all joints share diagonal U=V=I with different concentrations
+    J = 23
+    S = torch.tensor([[5.0, 3.0, 1.0]] * 8 + [[0.3, 0.2, 0.1]] * 8 + [[80.0, 60.0, 50.0]] * 7)[None]
+    U = torch.eye(3).expand(1, J, 3, 3).contiguous(); V = U.clone()
+    N = 20000
+    torch.manual_seed(0)
+    R, stats = hp.pose_matrix_fisher_sampling_torch(U.cuda(), S.cuda(), V.cuda(), N, return_stats=True)
+    assert int(stats[2]) == 0
+    acc_rate = int(stats[1]) / int(stats[0])
+    g = torch.Generator().manual_seed(1)
+    Ro = sampler_oracle.sample(U[:, :3].contiguous()[:, [0, 1, 2]], S[:, [0, 8, 16]], V[:, [0, 8, 16]], N, generator=g)
+    Rc = R.cpu()
+    assert (torch.det(Rc) - 1).abs().max() < 1e-5
+    for k, j0 in enumerate((0, 8, 16)):
+        mean_gpu = Rc[0, :, j0:j0 + 7].reshape(-1, 3, 3).mean(0)            # 7 joints x N samples
+        mean_ref = Ro[0, :, k].mean(0)
+        # Monte-Carlo error of a mean of N bounded entries ~ 1/sqrt(N) * O(0.5)
+        assert (mean_gpu - mean_ref).abs().max() < 4 * 0.6 / np.sqrt(N), (k, mean_gpu, mean_ref)
+        # analytic check at S=(5,3,1): diag E[R] = (0.8463, 0.7967, 0.7734)
+        if k == 0:
+            assert (torch.diagonal(mean_gpu) - torch.tensor([0.8463, 0.7967, 0.7734])).abs().max() < 5e-3
+    assert 0.40 < acc_rate < 0.80            # reference acceptance 0.43-0.73 across kappa
+    # different calls draw different streams; same seed reproduces
+    torch.manual_seed(0)
+    R2 = hp.pose_matrix_fisher_sampling_torch(U.cuda(), S.cuda(), V.cuda(), 64)
+    R3 = hp.pose_matrix_fisher_sampling_torch(U.cuda(), S.cuda(), V.cuda(), 64)
+    torch.manual_seed(0)
+    R4 = hp.pose_matrix_fisher_sampling_torch(U.cuda(), S.cuda(), V.cuda(), 64)
+    assert torch.equal(R2, R4) and not torch.equal(R2, R3)
+
+
+def test_full_size_properties(built_lib):
+    """BASELINE configs[1]/[4] sizes: validity of every rotation, no exhausted chains."""
+    import hierarchicalprobabilistic3dhuman_b200 as hp
+    for B, N, lo, hi in ((64, 100, 1e-2, 5e2), (128, 500, 50.0, 500.0)):
+        U, S, V = (torch.from_numpy(a).cuda() for a in syn.synthetic_usv(B, seed=B, s_lo=lo, s_hi=hi))
+        R, stats = hp.pose_matrix_fisher_sampling_torch(U, S, V, N, return_stats=True)
+        assert int(stats[2]) == 0
+        assert (torch.linalg.det(R) - 1).abs().max() < 1e-4
+        assert (R.transpose(-1, -2) @ R - torch.eye(3, device="cuda")).abs().max() < 1e-4

@@ -1,0 +1,67 @@
+"""The oracle restatements reproduce the reference's own outputs (golden fixtures written by
+oracle/make_golden.py from the unmodified reference). CPU only."""
+import numpy as np
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import net_oracle, sampler_oracle
+from hierarchicalprobabilistic3dhuman_b200 import synthetic as syn
+
+
+def _checksum(t):
+    t = torch.as_tensor(t).double()
+    return np.array([t.sum().item(), t.abs().sum().item(), (t * t).sum().item()])
+
+
+def test_synthetic_inputs_reproduce_checksums():
+    g = load_golden("net_b4")
+    x = syn.synthetic_proxy_rep(4, seed=0)
+    np.testing.assert_allclose(_checksum(x), g["x_checksum"], rtol=1e-12)
+    sd = syn.synthetic_state_dict(0)
+    s = np.sum([_checksum(v.float())[1] for k, v in sorted(sd.items())])
+    np.testing.assert_allclose(s, g["sd_checksum"], rtol=1e-12)
+
+
+def test_net_oracle_matches_reference_golden():
+    g = load_golden("net_b4")
+    sd = syn.synthetic_state_dict(0)
+    x = torch.from_numpy(syn.synthetic_proxy_rep(4, seed=0))
+    with torch.no_grad():
+        feats = net_oracle.encoder_forward(sd, x)
+        h = net_oracle.head_forward(sd, feats, syn.SMPL_PARENTS)
+    # same code path / same LAPACK in the same image: bit-exact here; tolerance covers thread-count effects
+    assert rel_err(feats, g["feats"]) < 1e-5
+    for k in ("F", "S", "mode"):
+        assert rel_err(h[k], g[k]) < 1e-4, k
+    assert rel_err(h["shape_params"][:, :10], g["shape_loc"]) < 1e-5
+    assert rel_err(torch.exp(h["shape_params"][:, 10:]), g["shape_scale"]) < 1e-5
+    assert rel_err(h["glob"], g["glob"]) < 1e-5 and rel_err(h["cam"], g["cam"]) < 1e-5
+    assert rel_err(net_oracle.rot6d_to_rotmat(h["glob"]), g["glob_rotmats"]) < 1e-5
+
+
+def test_head_oracle_matches_reference_golden_b64():
+    g = load_golden("head_b64")
+    sd = syn.synthetic_state_dict(0)
+    rs = np.random.RandomState(7)
+    feats = torch.from_numpy(np.abs(rs.normal(0, 1.0, size=(64, 512))).astype(np.float32))
+    with torch.no_grad():
+        h = net_oracle.head_forward(sd, feats, syn.SMPL_PARENTS)
+    for k in ("F", "U", "S", "V", "mode"):
+        assert rel_err(h[k], g[k]) < 1e-5, k
+
+
+def test_sampler_oracle_matches_reference_golden():
+    for name in ("sampler_usv_b4_n8", "sampler_head_b4_n8", "sampler_lowk_b2_n100", "sampler_highk_b2_n100"):
+        g = load_golden(name)
+        U, S, V = (torch.from_numpy(g[k]) for k in ("U", "S", "V"))
+        N = int(g["N"])
+        torch.manual_seed(int(g["seed"]))
+        eps, w = sampler_oracle.draw_noise(U.shape[0], U.shape[1], N)
+        np.testing.assert_allclose(_checksum(eps) + _checksum(w), g["noise_checksum"], rtol=1e-10)
+        R, acc = sampler_oracle.sample_with_noise(U, S, V, N, eps, w)
+        assert rel_err(R, g["R"]) < 1e-6, name
+        assert np.array_equal(acc.numpy(), g["accepted"])
+        # rotation validity
+        assert (torch.det(R) - 1).abs().max() < 1e-5
+        eye = torch.eye(3)
+        assert (R.transpose(-1, -2) @ R - eye).abs().max() < 1e-5
