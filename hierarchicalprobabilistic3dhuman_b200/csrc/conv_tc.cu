@@ -1,0 +1,518 @@
+// ResNet-18 encoder, fast mode: every convolution is an im2col-free implicit GEMM on the 5th-gen
+// tensor cores (tcgen05.mma, fp16 operands, fp32 accumulation in TMEM), operands staged by TMA.
+//
+//   D[128 output pixels][BN output channels] += A[128 pixels][64 k] * W[BN][64 k]^T      per k-block
+//
+// * activations live in HBM as NHWC fp16; a 4-D tensor map {C, W, H, N} with box {64, BW, BH, BIMG}
+//   (BW*BH*BIMG = 128) delivers, for filter tap (kh,kw) and channel block c, exactly the A tile of that
+//   tap: the box is shifted by (kw-pad, kh-pad) and TMA zero-fills everything outside the image, which
+//   *is* the convolution's zero padding. No im2col buffer ever exists.
+// * stride-2 convolutions read through "phase" tensor maps (one per input row/column parity: base
+//   pointer offset + doubled strides), which turns them into stride-1 problems.
+// * the 7x7/2 stem on 18 channels: input channels are padded to 32 and two adjacent pixels form one
+//   64-channel "pixel pair", so each filter row is 4 k-blocks (taps -1..6, tap -1 has zero weights).
+// * weights are repacked [Cout][K] (K-major, BN folded into them), 2-D tensor map, box {64, BN}.
+// * both operand tiles use the 128-byte swizzle (TMA writes it, the UMMA descriptor reads it).
+// * warp-specialised persistent kernel (canonical Blackwell GEMM anatomy): warp 0 = TMA producer,
+//   warp 1 = MMA issuer (one thread), warp 2 = TMEM allocator, warps 4-7 = epilogue
+//   (tcgen05.ld -> +bias (+residual) -> ReLU -> fp16 NHWC store). Two TMEM accumulators let the
+//   epilogue of tile i overlap the main loop of tile i+1; a STAGES-deep smem ring feeds the MMAs.
+#include "encoder.cuh"
+#include "tc_common.cuh"
+#include <vector>
+#include <algorithm>
+
+using namespace hp3d;
+using namespace hp3d::tc;
+
+namespace {
+
+constexpr int MAX_KB = 72;
+constexpr int BLOCK_M = 128, BLOCK_K = 64;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
+
+struct KBlock { int8_t map, dx, dy, pad; int16_t c, pad2; };   // A-tile source of one k-block
+
+struct ConvTcArgs {
+  int num_kb;
+  int tiles_m, tiles_n;
+  int tiles_x, tiles_y;        // spatial tiles per image
+  int BW, BH, BIMG;            // output-pixel box of one M tile (BW*BH*BIMG == 128)
+  int N, Ho, Wo, Cout;         // N = number of images actually present
+  const float* bias;
+  const __half* residual;
+  __half* out;
+  int relu;
+  KBlock kb[MAX_KB];
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;
+  static constexpr int TOTAL = BIAS_OFFSET + 2 * BN * 4 + 1024;   // + slack for 1024-byte alignment
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvTcArgs args) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + L::BIAS_OFFSET);   // [2][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = args.tiles_m * args.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0); tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmA3);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<2 * BN>(tmem_base_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % args.tiles_n, mt = tile / args.tiles_n;
+        const int tx = mt % args.tiles_x, ty = (mt / args.tiles_x) % args.tiles_y;
+        const int n0 = (mt / (args.tiles_x * args.tiles_y)) * args.BIMG;
+        const int ox0 = tx * args.BW, oy0 = ty * args.BH;
+        for (int kb = 0; kb < args.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          const KBlock k = args.kb[kb];
+          const CUtensorMap* ma = (k.map == 0) ? &tmA0 : (k.map == 1) ? &tmA1 : (k.map == 2) ? &tmA2 : &tmA3;
+          tma_load_4d(a_dst, ma, &full_bar[stage], k.c, ox0 + k.dx, oy0 + k.dy, n0);
+          tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BLOCK_K, nt * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < args.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint64_t a_desc = umma_desc_sw128(a_addr);
+          const uint64_t b_desc = umma_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);                       // frees the smem slot when these MMAs retire
+          if (kb == args.num_kb - 1) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================================================== epilogue (128 threads = 128 TMEM lanes)
+    const int ew = warp - 4;                    // == warp % 4: the TMEM lane quarter this warp may access
+    const int row = ew * 32 + lane;
+    const int et = threadIdx.x - 128;
+    int acc = 0; uint32_t acc_phase = 0;
+    const int img_px = args.BW * args.BH;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int nt = tile % args.tiles_n, mt = tile / args.tiles_n;
+      const int tx = mt % args.tiles_x, ty = (mt / args.tiles_x) % args.tiles_y;
+      const int n0 = (mt / (args.tiles_x * args.tiles_y)) * args.BIMG;
+      const int il = row / img_px, rem = row - il * img_px;
+      const int yl = rem / args.BW, xl = rem - yl * args.BW;
+      const int n = n0 + il;
+      const size_t pix = ((size_t)n * args.Ho + (ty * args.BH + yl)) * args.Wo + (tx * args.BW + xl);
+      const size_t off = pix * args.Cout + (size_t)nt * BN;
+      float* bsm = bias_s + acc * BN;
+      if (et < BN) bsm[et] = args.bias[nt * BN + et];
+      asm volatile("bar.sync 1, 128;" ::: "memory");            // epilogue-only named barrier
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + ch * 32, r);
+        tmem_ld_wait();
+        if (n < args.N) {
+          const uint4* res = args.residual ? reinterpret_cast<const uint4*>(args.residual + off + ch * 32) : nullptr;
+          uint4* dst = reinterpret_cast<uint4*>(args.out + off + ch * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[q * 8 + e]) + bsm[ch * 32 + q * 8 + e];
+            if (res) {
+              const uint4 rv = res[q];
+              const __half2* h = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+            }
+            if (args.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+            dst[q] = o;
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc<2 * BN>(tmem_base); }
+}
+
+// ---------------------------------------------------------------- elementwise helpers (fp16 NHWC)
+__global__ void __launch_bounds__(256) nchw_f32_to_nhwc32_f16_kernel(const float* __restrict__ x, int C, int HW,
+                                                                     __half* __restrict__ y) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.y, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int c = ty; c < 32; c += 8) tile[c][tx] = (c < C && p0 + tx < HW) ? x[((size_t)n * C + c) * HW + p0 + tx] : 0.f;
+  __syncthreads();
+  for (int p = ty; p < 32; p += 8)
+    if (p0 + p < HW) y[((size_t)n * HW + p0 + p) * 32 + tx] = __float2half_rn(tile[tx][p]);
+}
+
+__global__ void __launch_bounds__(256) maxpool3x3s2_f16_kernel(const __half* __restrict__ in, int H, int W, int C, int Ho,
+                                                               int Wo, __half* __restrict__ out, size_t total8) {
+  // one thread = 8 channels of one output pixel
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int c8 = C / 8;
+  const int c = (int)(i % c8) * 8;
+  size_t r = i / c8;
+  const int ox = (int)(r % Wo); r /= Wo;
+  const int oy = (int)(r % Ho);
+  const int n = (int)(r / Ho);
+  __half2 m[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) m[e] = __float2half2_rn(-65504.f);
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int iy = oy * 2 - 1 + dy;
+    if (iy < 0 || iy >= H) continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int ix = ox * 2 - 1 + dx;
+      if (ix < 0 || ix >= W) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(in + (((size_t)n * H + iy) * W + ix) * C + c);
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) m[e] = __hmax2(m[e], h[e]);
+    }
+  }
+  uint4 o;
+  __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) oh[e] = m[e];
+  *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oy) * Wo + ox) * C + c) = o;
+}
+
+__global__ void __launch_bounds__(256) avgpool_f16_kernel(const __half* __restrict__ in, int HW, int C,
+                                                          float* __restrict__ out) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += __half2float(in[((size_t)n * HW + p) * C + c]);
+    out[(size_t)n * C + c] = s / (float)HW;
+  }
+}
+
+// ---------------------------------------------------------------- host-side plan
+struct TcConv {
+  __half* w = nullptr;        // [Cout][Ktot] K-major fp16 (BN folded)
+  float* bias = nullptr;      // [Cout]
+  int cin, cout, k, stride, pad, ktot;
+  bool stem = false;
+  CUtensorMap tmB;            // weights (encoded at create time)
+  int bn;
+};
+
+struct EncoderTc {
+  TcConv stem, conv[4][2][2], down[4];
+  bool has_down[4] = {false, false, false, false};
+  int num_sms = 148;
+};
+
+int make_tc_conv(const hp3d_conv_bn& c, float eps, bool stem, TcConv& L) {
+  std::vector<float> w_khwc, bias;
+  // fold BN in fp64, layout [kh][kw][cin][cout]
+  int rc = fold_conv_bn(c, eps, c.cin, w_khwc, bias);
+  if (rc) return rc;
+  L.cin = c.cin; L.cout = c.cout; L.k = c.k; L.stride = c.stride; L.pad = c.pad; L.stem = stem;
+  L.bn = (c.cout == 64) ? 64 : 128;
+  std::vector<__half> wk;
+  if (!stem) {
+    L.ktot = c.k * c.k * c.cin;                       // K index = (kh*k + kw)*cin + ci
+    wk.resize((size_t)c.cout * L.ktot);
+    for (int o = 0; o < c.cout; ++o)
+      for (int t = 0; t < c.k * c.k; ++t)
+        for (int i = 0; i < c.cin; ++i)
+          wk[(size_t)o * L.ktot + (size_t)t * c.cin + i] = __float2half_rn(w_khwc[((size_t)t * c.cin + i) * c.cout + o]);
+  } else {
+    // K index = kh*256 + (dp+2)*64 + e*32 + ci with input column 2(x+dp)+e = 2x + kw - 3  =>  kw = 2dp + e + 3
+    L.ktot = 7 * 256;
+    wk.assign((size_t)c.cout * L.ktot, __float2half_rn(0.f));
+    for (int o = 0; o < c.cout; ++o)
+      for (int kh = 0; kh < 7; ++kh)
+        for (int dp = -2; dp <= 1; ++dp)
+          for (int e = 0; e < 2; ++e) {
+            const int kw = 2 * dp + e + 3;
+            if (kw < 0 || kw > 6) continue;
+            for (int i = 0; i < c.cin; ++i)
+              wk[(size_t)o * L.ktot + kh * 256 + (dp + 2) * 64 + e * 32 + i] =
+                  __float2half_rn(w_khwc[(((size_t)kh * 7 + kw) * c.cin + i) * c.cout + o]);
+          }
+  }
+  rc = upload(&L.w, wk.data(), wk.size());
+  rc = rc ? rc : upload(&L.bias, bias.data(), bias.size());
+  if (rc) return rc;
+  const uint64_t dims[2] = {(uint64_t)L.ktot, (uint64_t)L.cout};
+  const uint64_t strides[1] = {(uint64_t)L.ktot * 2};
+  const uint32_t box[2] = {64, (uint32_t)L.bn};
+  return make_tmap_f16(&L.tmB, L.w, 2, dims, strides, box);
+}
+
+// Launch one convolution: in [N][H][W][Cin_mem] fp16 (Cin_mem = 32 for the stem input), out [N][Ho][Wo][Cout].
+int run_tc_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N, int H, int W, const __half* residual,
+                int relu, __half* out, cudaStream_t s) {
+  const int Ho = H / L.stride, Wo = W / L.stride;
+  const uint64_t Np = (uint64_t)((N + 1) & ~1);   // buffers hold an even number of images (layer4 tiles span two)
+  ConvTcArgs a;
+  memset(&a, 0, sizeof(a));
+  if (Wo >= 16 && Ho >= 8 && Wo % 16 == 0 && Ho % 8 == 0) { a.BW = 16; a.BH = 8; a.BIMG = 1; }
+  else if (Wo == 8 && Ho == 8) { a.BW = 8; a.BH = 8; a.BIMG = 2; }
+  else { set_error("conv_tc: unsupported output size %dx%d", Ho, Wo); return -1; }
+  a.tiles_x = Wo / a.BW; a.tiles_y = Ho / a.BH;
+  a.tiles_m = a.tiles_x * a.tiles_y * cdiv(N, a.BIMG);
+  a.tiles_n = L.cout / L.bn;
+  a.N = N; a.Ho = Ho; a.Wo = Wo; a.Cout = L.cout;
+  a.bias = L.bias; a.residual = residual; a.out = out; a.relu = relu;
+  CUtensorMap tmA[4];
+  const uint32_t box[4] = {64, (uint32_t)a.BW, (uint32_t)a.BH, (uint32_t)a.BIMG};
+  int nmaps = 0;
+  int nk = 0;
+  if (L.stem) {
+    // pixel-pair view of [N][H][W][32]: {64, W/2, H/2 (row parity ph), N}
+    for (int ph = 0; ph < 2; ++ph) {
+      const uint64_t dims[4] = {64, (uint64_t)W / 2, (uint64_t)H / 2, Np};
+      const uint64_t st[3] = {128, (uint64_t)2 * W * 64, (uint64_t)H * W * 64};
+      int rc = make_tmap_f16(&tmA[ph], in + (size_t)ph * W * 32, 4, dims, st, box);
+      if (rc) return rc;
+    }
+    nmaps = 2;
+    for (int kh = 0; kh < 7; ++kh) {
+      const int o = kh - 3;
+      const int ph = ((o % 2) + 2) % 2;
+      const int dy = (o - ph) / 2;
+      for (int dp = -2; dp <= 1; ++dp) {
+        KBlock& k = a.kb[nk++];
+        k.map = (int8_t)ph; k.dx = (int8_t)dp; k.dy = (int8_t)dy; k.c = 0;
+      }
+    }
+  } else if (L.stride == 1) {
+    const uint64_t dims[4] = {(uint64_t)L.cin, (uint64_t)W, (uint64_t)H, Np};
+    const uint64_t st[3] = {(uint64_t)L.cin * 2, (uint64_t)W * L.cin * 2, (uint64_t)H * W * L.cin * 2};
+    int rc = make_tmap_f16(&tmA[0], in, 4, dims, st, box);
+    if (rc) return rc;
+    nmaps = 1;
+    for (int kh = 0; kh < L.k; ++kh)
+      for (int kw = 0; kw < L.k; ++kw)
+        for (int c = 0; c < L.cin; c += 64) {
+          KBlock& k = a.kb[nk++];
+          k.map = 0; k.dx = (int8_t)(kw - L.pad); k.dy = (int8_t)(kh - L.pad); k.c = (int16_t)c;
+        }
+  } else {   // stride 2: parity maps, map index = py*2 + px
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const uint64_t dims[4] = {(uint64_t)L.cin, (uint64_t)W / 2, (uint64_t)H / 2, Np};
+        const uint64_t st[3] = {(uint64_t)2 * L.cin * 2, (uint64_t)2 * W * L.cin * 2, (uint64_t)H * W * L.cin * 2};
+        int rc = make_tmap_f16(&tmA[py * 2 + px], in + ((size_t)py * W + px) * L.cin, 4, dims, st, box);
+        if (rc) return rc;
+      }
+    nmaps = 4;
+    for (int kh = 0; kh < L.k; ++kh)
+      for (int kw = 0; kw < L.k; ++kw) {
+        const int oy = kh - L.pad, ox = kw - L.pad;
+        const int py = ((oy % 2) + 2) % 2, px = ((ox % 2) + 2) % 2;
+        for (int c = 0; c < L.cin; c += 64) {
+          KBlock& k = a.kb[nk++];
+          k.map = (int8_t)(py * 2 + px); k.dx = (int8_t)((ox - px) / 2); k.dy = (int8_t)((oy - py) / 2); k.c = (int16_t)c;
+        }
+      }
+  }
+  for (int i = nmaps; i < 4; ++i) tmA[i] = tmA[0];
+  if (nk > MAX_KB || nk * 64 != L.ktot) { set_error("conv_tc: k-block table mismatch (%d blocks, K=%d)", nk, L.ktot); return -1; }
+  a.num_kb = nk;
+  const int grid = std::min(a.tiles_m * a.tiles_n, E->num_sms);
+  if (L.bn == 64) {
+    using SL = SmemLayout<64, 6>;
+    static bool set = false;
+    if (!set) { HP3D_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL)); set = true; }
+    conv_tc_kernel<64, 6><<<grid, 256, SL::TOTAL, s>>>(tmA[0], tmA[1], tmA[2], tmA[3], L.tmB, a);
+  } else {
+    using SL = SmemLayout<128, 5>;
+    static bool set = false;
+    if (!set) { HP3D_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL)); set = true; }
+    conv_tc_kernel<128, 5><<<grid, 256, SL::TOTAL, s>>>(tmA[0], tmA[1], tmA[2], tmA[3], L.tmB, a);
+  }
+  return launch_status("conv_tc_kernel");
+}
+
+size_t act_bytes(int N, int H, int W, int C) { return align_up((size_t)N * H * W * C * 2, 1024); }
+
+}  // namespace
+
+namespace hp3d {
+
+int encoder_tc_create(const hp3d_encoder_weights* w, void** out) {
+  if (!encode_fn()) { set_error("HP3D_ENC_FAST needs cuTensorMapEncodeTiled (driver >= 12.0)"); return -3; }
+  EncoderTc* E = new EncoderTc();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&E->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  int rc = make_tc_conv(w->stem, w->bn_eps, true, E->stem);
+  const int planes[4] = {64, 128, 256, 512};
+  int inpl = 64;
+  for (int l = 0; l < 4 && !rc; ++l)
+    for (int b = 0; b < 2 && !rc; ++b) {
+      const hp3d_conv_bn& c1 = w->conv[l][b][0];
+      const hp3d_conv_bn& c2 = w->conv[l][b][1];
+      const int stride = (l > 0 && b == 0) ? 2 : 1;
+      if (c1.cin != inpl || c1.cout != planes[l] || c1.k != 3 || c1.stride != stride || c1.pad != 1 || c2.cin != planes[l] ||
+          c2.cout != planes[l] || c2.k != 3 || c2.stride != 1 || c2.pad != 1) {
+        set_error("encoder_tc_create: layer%d.%d is not a ResNet-18 BasicBlock", l + 1, b); rc = -1; break;
+      }
+      rc = make_tc_conv(c1, w->bn_eps, false, E->conv[l][b][0]);
+      rc = rc ? rc : make_tc_conv(c2, w->bn_eps, false, E->conv[l][b][1]);
+      if (b == 0 && l > 0 && !rc) {
+        const hp3d_conv_bn& d = w->down[l];
+        if (!d.w || d.cin != inpl || d.cout != planes[l] || d.k != 1 || d.stride != 2 || d.pad != 0) {
+          set_error("encoder_tc_create: layer%d downsample must be 1x1/2", l + 1); rc = -1; break;
+        }
+        rc = make_tc_conv(d, w->bn_eps, false, E->down[l]);
+        E->has_down[l] = true;
+      }
+      inpl = planes[l];
+    }
+  if (rc) { encoder_tc_destroy(E); return rc; }
+  *out = E;
+  return 0;
+}
+
+void encoder_tc_destroy(void* p) {
+  if (!p) return;
+  EncoderTc* E = (EncoderTc*)p;
+  auto fr = [](TcConv& L) { cudaFree(L.w); cudaFree(L.bias); };
+  fr(E->stem);
+  for (int l = 0; l < 4; ++l) { for (int b = 0; b < 2; ++b) { fr(E->conv[l][b][0]); fr(E->conv[l][b][1]); } fr(E->down[l]); }
+  delete E;
+}
+
+size_t encoder_tc_workspace_bytes(const void*, int B, int H, int W) {
+  const int Bp = (B + 1) & ~1;   // layer4 tiles span two images
+  return act_bytes(Bp, H, W, 32) + act_bytes(Bp, H / 2, W / 2, 64) + 4 * act_bytes(Bp, H / 4, W / 4, 64);
+}
+
+int encoder_tc_forward(const void* p, const float* x, int B, int H, int W, float* feats, void* workspace,
+                       size_t workspace_bytes, float* taps, cudaStream_t s) {
+  const EncoderTc* E = (const EncoderTc*)p;
+  if (H != 256 || W != 256) { set_error("HP3D_ENC_FAST supports 256x256 proxy representations (DATA.PROXY_REP_SIZE)"); return -1; }
+  const int Bp = (B + 1) & ~1;
+  char* ws = (char*)workspace;
+  __half* xin = (__half*)ws; ws += act_bytes(Bp, H, W, 32);
+  __half* stem = (__half*)ws; ws += act_bytes(Bp, H / 2, W / 2, 64);
+  __half* buf[4];
+  for (int i = 0; i < 4; ++i) { buf[i] = (__half*)ws; ws += act_bytes(Bp, H / 4, W / 4, 64); }
+  nchw_f32_to_nhwc32_f16_kernel<<<dim3(cdiv(H * W, 32), B), 256, 0, s>>>(x, 18, H * W, xin);
+  int rc = launch_status("nchw_f32_to_nhwc32_f16_kernel");
+  if (rc) return rc;
+  rc = run_tc_conv(E, E->stem, xin, B, H, W, nullptr, 1, stem, s);
+  if (rc) return rc;
+  int ch = H / 2, cw = W / 2;
+  rc = tap_copy_f16(stem, (size_t)B * ch * cw * 64, &taps, s);
+  if (rc) return rc;
+  {
+    const size_t total8 = (size_t)B * (ch / 2) * (cw / 2) * 64 / 8;
+    maxpool3x3s2_f16_kernel<<<(unsigned)((total8 + 255) / 256), 256, 0, s>>>(stem, ch, cw, 64, ch / 2, cw / 2, buf[0], total8);
+    rc = launch_status("maxpool3x3s2_f16_kernel");
+    if (rc) return rc;
+    ch /= 2; cw /= 2;
+    rc = tap_copy_f16(buf[0], total8 * 8, &taps, s);
+    if (rc) return rc;
+  }
+  __half* cur = buf[0];
+  int free_idx[3] = {1, 2, 3};
+  int C = 64;
+  for (int l = 0; l < 4; ++l)
+    for (int b = 0; b < 2; ++b) {
+      const TcConv& c1 = E->conv[l][b][0];
+      const TcConv& c2 = E->conv[l][b][1];
+      __half* t = buf[free_idx[0]];
+      __half* y = buf[free_idx[1]];
+      __half* d = buf[free_idx[2]];
+      rc = run_tc_conv(E, c1, cur, B, ch, cw, nullptr, 1, t, s);
+      if (rc) return rc;
+      const int oh = ch / c1.stride, ow = cw / c1.stride;
+      const __half* identity = cur;
+      if (b == 0 && E->has_down[l]) {
+        rc = run_tc_conv(E, E->down[l], cur, B, ch, cw, nullptr, 0, d, s);
+        if (rc) return rc;
+        identity = d;
+      }
+      rc = run_tc_conv(E, c2, t, B, oh, ow, identity, 1, y, s);
+      if (rc) return rc;
+      int cur_idx = 0;
+      for (int i = 0; i < 4; ++i) if (buf[i] == cur) cur_idx = i;
+      const int y_idx = free_idx[1];
+      free_idx[1] = cur_idx;
+      cur = buf[y_idx];
+      ch = oh; cw = ow; C = c1.cout;
+      rc = tap_copy_f16(cur, (size_t)B * ch * cw * C, &taps, s);
+      if (rc) return rc;
+    }
+  avgpool_f16_kernel<<<B, 256, 0, s>>>(cur, ch * cw, C, feats);
+  return launch_status("avgpool_f16_kernel");
+}
+
+}  // namespace hp3d

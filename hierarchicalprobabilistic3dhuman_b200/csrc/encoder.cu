@@ -11,6 +11,7 @@
 // 18 -> 20/32 channels), weights [kh][kw][cin][cout] so both GEMM operands are contiguous along K/N.
 #include "common.cuh"
 #include "encoder.cuh"
+#include <cuda_fp16.h>
 #include <vector>
 #include <math.h>
 
@@ -138,9 +139,27 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const T* __restrict__ in, 
   }
 }
 
+template <typename T>
+__global__ void tap_copy_kernel(const T* __restrict__ src, size_t n, float* __restrict__ dst) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = (float)src[i];
+}
+
 }  // namespace
 
 namespace hp3d {
+
+int tap_copy_f32(const float* src, size_t count, float** taps, cudaStream_t s) {
+  if (!*taps) return 0;
+  tap_copy_kernel<float><<<1184, 256, 0, s>>>(src, count, *taps);
+  *taps += count;
+  return launch_status("tap_copy_kernel");
+}
+int tap_copy_f16(const void* src, size_t count, float** taps, cudaStream_t s) {
+  if (!*taps) return 0;
+  tap_copy_kernel<__half><<<1184, 256, 0, s>>>((const __half*)src, count, *taps);
+  *taps += count;
+  return launch_status("tap_copy_kernel");
+}
 
 int fold_conv_bn(const hp3d_conv_bn& c, float eps, int cin_pad, std::vector<float>& w_khwc, std::vector<float>& bias) {
   if (!c.w || !c.bn_w || !c.bn_b || !c.bn_mean || !c.bn_var) { set_error("encoder: null conv/bn pointer"); return -1; }
@@ -260,11 +279,16 @@ static int run_conv(const ConvLayer& L, const float* in, int B, int H, int W, co
 
 extern "C" int hp3d_encoder_forward(const hp3d_encoder* h, const float* x, int B, int H, int W, float* feats,
                                     void* workspace, size_t workspace_bytes, void* stream_) {
+  return hp3d_encoder_forward_taps(h, x, B, H, W, feats, workspace, workspace_bytes, nullptr, stream_);
+}
+
+extern "C" int hp3d_encoder_forward_taps(const hp3d_encoder* h, const float* x, int B, int H, int W, float* feats,
+                                         void* workspace, size_t workspace_bytes, float* taps, void* stream_) {
   HP3D_ARG(h && x && feats && workspace, "null argument");
   HP3D_ARG(B > 0 && H >= 32 && W >= 32 && H % 32 == 0 && W % 32 == 0, "H and W must be multiples of 32");
   HP3D_ARG(workspace_bytes >= hp3d_encoder_workspace_bytes(h, B, H, W), "workspace too small");
   cudaStream_t s = (cudaStream_t)stream_;
-  if (h->mode == HP3D_ENC_FAST) return encoder_tc_forward(h->tc, x, B, H, W, feats, workspace, workspace_bytes, s);
+  if (h->mode == HP3D_ENC_FAST) return encoder_tc_forward(h->tc, x, B, H, W, feats, workspace, workspace_bytes, taps, s);
   char* ws = (char*)workspace;
   float* xin = (float*)ws; ws += align_up((size_t)B * H * W * 20 * 4, 256);
   float* stem = (float*)ws; ws += align_up((size_t)B * (H / 2) * (W / 2) * 64 * 4, 256);
@@ -277,12 +301,16 @@ extern "C" int hp3d_encoder_forward(const hp3d_encoder* h, const float* x, int B
   rc = run_conv(h->stem, xin, B, H, W, nullptr, 1, stem, s);
   if (rc) return rc;
   int ch = H / 2, cw = W / 2;
+  rc = tap_copy_f32(stem, (size_t)B * ch * cw * 64, &taps, s);
+  if (rc) return rc;
   {
     const size_t total = (size_t)B * (ch / 2) * (cw / 2) * 64;
     maxpool3x3s2_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(stem, ch, cw, 64, ch / 2, cw / 2, buf[0], total);
     rc = launch_status("maxpool3x3s2_kernel");
     if (rc) return rc;
     ch /= 2; cw /= 2;
+    rc = tap_copy_f32(buf[0], total, &taps, s);
+    if (rc) return rc;
   }
   float* cur = buf[0];
   int free_idx[3] = {1, 2, 3};
@@ -312,6 +340,8 @@ extern "C" int hp3d_encoder_forward(const hp3d_encoder* h, const float* x, int B
       free_idx[1] = cur_idx;
       cur = buf[y_idx];
       ch = oh; cw = ow; C = c1.cout;
+      rc = tap_copy_f32(cur, (size_t)B * ch * cw * C, &taps, s);
+      if (rc) return rc;
     }
   }
   avgpool_kernel<float><<<B, 256, 0, s>>>(cur, ch * cw, C, feats);

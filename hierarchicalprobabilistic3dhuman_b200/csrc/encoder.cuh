@@ -8,5 +8,8 @@ int encoder_tc_create(const hp3d_encoder_weights* w, void** out);
 void encoder_tc_destroy(void* p);
 size_t encoder_tc_workspace_bytes(const void* p, int B, int H, int W);
 int encoder_tc_forward(const void* p, const float* x_nchw, int B, int H, int W, float* feats, void* workspace,
-                       size_t workspace_bytes, cudaStream_t stream);
+                       size_t workspace_bytes, float* taps, cudaStream_t stream);
+// append `count` activation values (converted to fp32) to the debug tap buffer
+int tap_copy_f32(const float* src, size_t count, float** taps, cudaStream_t s);
+int tap_copy_f16(const void* src, size_t count, float** taps, cudaStream_t s);
 }  // namespace hp3d

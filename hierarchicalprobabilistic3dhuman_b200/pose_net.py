@@ -169,6 +169,34 @@ class PoseMFShapeGaussianNet(nn.Module):
                                               _lib.stream_ptr()), "hp3d_encoder_forward")
         return feats
 
+    def encode_taps(self, input):
+        """Debug/parity helper: (feats, [stem, pool, layer1.0, ..., layer4.1]) with every activation as an
+        fp32 NHWC tensor (hp3d_encoder_forward_taps)."""
+        _lib.require_cuda(input, "input")
+        dev = input.device
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        enc, _ = self._build_handles(key, True)
+        x = input.detach().to(torch.float32).contiguous()
+        B, C, H, W = x.shape
+        shapes = [(B, H // 2, W // 2, 64), (B, H // 4, W // 4, 64)]
+        for li, pl in enumerate((64, 128, 256, 512)):
+            shapes += [(B, H // (4 << li), W // (4 << li), pl)] * 2
+        total = sum(int(np.prod(s)) for s in shapes)
+        taps = torch.empty(total, device=dev, dtype=torch.float32)
+        feats = torch.empty(B, 512, device=dev, dtype=torch.float32)
+        L = _lib.lib()
+        with torch.cuda.device(dev):
+            nbytes = L.hp3d_encoder_workspace_bytes(enc, B, H, W)
+            ws = self._ws.get(nbytes, dev)
+            _lib.check(L.hp3d_encoder_forward_taps(enc, x.data_ptr(), B, H, W, feats.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                   taps.data_ptr(), _lib.stream_ptr()), "hp3d_encoder_forward_taps")
+        out, o = [], 0
+        for s in shapes:
+            n = int(np.prod(s))
+            out.append(taps[o:o + n].view(*s))
+            o += n
+        return feats, out
+
     def head(self, input_feats, teacher=None):
         _lib.require_cuda(input_feats, "input_feats")
         dev = input_feats.device

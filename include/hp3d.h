@@ -133,6 +133,11 @@ size_t hp3d_encoder_workspace_bytes(const hp3d_encoder* h, int B, int H, int W);
 /* x [B*18*H*W] fp32 NCHW (the reference's input layout, predict/...:100) -> feats [B*512] */
 int hp3d_encoder_forward(const hp3d_encoder* h, const float* x_nchw, int B, int H, int W, float* feats,
                          void* workspace, size_t workspace_bytes, void* stream);
+/* same, additionally dumping every post-activation tensor as fp32 NHWC into `taps` in the order
+ * stem (B,H/2,W/2,64) | maxpool (B,H/4,W/4,64) | layer1.0 | layer1.1 | ... | layer4.1  (parity debugging of the
+ * per-layer kernels against models/resnet.py:203-212; taps == NULL behaves like hp3d_encoder_forward). */
+int hp3d_encoder_forward_taps(const hp3d_encoder* h, const float* x_nchw, int B, int H, int W, float* feats,
+                              void* workspace, size_t workspace_bytes, float* taps, void* stream);
 
 #ifdef __cplusplus
 }
