@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Benchmark of the probabilistic-pose inference hot path (BASELINE.json metric: images/sec at
+B=256 per GPU, N_samples=100; plus SMPL-LBS HBM GB/s vs peak).
+
+  python bench.py --gpus 1 --steps 10 --warmup 3                      # own arm (CUDA, libhp3d)
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference --steps 3 --warmup 1               # the reference algorithm on host cores
+
+One step = one pass of the hot path over one batch of synthetic proxy representations per rank
+(weak scaling): ResNet-18 encoder -> hierarchical matrix-Fisher head -> rot6d -> mode SMPL ->
+matrix-Fisher sampler (N samples / image) -> SMPL on B*N meshes -> per-vertex uncertainty ->
+[N>1: in-place NCCL all-gather of (rotmats, betas, vertices), BASELINE configs[3]].
+`value` times that with inputs resident in HBM; `e2e` times the same call through the public API
+with HOST (pinned) inputs and a device->host read of the per-image results inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+LBS_BYTES_PER_MESH = 167592   # read v_posed 82,680 + rotmats 864 + J 288; write vertices 82,680 + joints 1,080
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="hp3d", choices=["hp3d", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--samples", type=int, default=100)
+    ap.add_argument("--encoder-mode", default="fast", choices=["fast", "parity"])
+    ap.add_argument("--ref-batch", type=int, default=4, help="images per step of the CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="full", choices=["full", "stats"],
+                    help="N>1: all-gather (rotmats, betas, vertices) [configs[3]] or per-image statistics only")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def cfg():
+    from types import SimpleNamespace as NS
+    return NS(MODEL=NS(NUM_IN_CHANNELS=18, NUM_RESNET_LAYERS=18, EMBED_DIM=256, DELTA_I=True, DELTA_I_WEIGHT=1.0,
+                       NUM_SMPL_BETAS=10))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def cpu_reference_step(sd, x, smpl_oracle, N, parents):
+    """The reference's algorithm for the path (oracle port, torch CPU, all host threads):
+    predict/predict_poseMF_shapeGaussian_net.py:102-165 composed batched as train/...:293-308."""
+    from oracle import net_oracle, sampler_oracle
+    B = x.shape[0]
+    with torch.no_grad():
+        feats = net_oracle.encoder_forward(sd, x)
+        h = net_oracle.head_forward(sd, feats, parents)
+        glob_R = net_oracle.rot6d_to_rotmat(h["glob"])
+        loc = h["shape_params"][:, :10]
+        mode = smpl_oracle.forward(loc, h["mode"], glob_R[:, None])
+        R = sampler_oracle.sample(h["U"], h["S"], h["V"], N)
+        out = smpl_oracle.forward(loc.repeat_interleave(N, 0), R.reshape(B * N, 23, 3, 3), glob_R.repeat_interleave(N, 0)[:, None])
+        v = out["vertices"].view(B, N, 6890, 3)
+        unc = (v - v.mean(1, keepdim=True)).norm(dim=-1).mean(1)
+    return unc, mode["vertices"]
+
+
+def time_cpu_reference(steps, warmup, ref_batch, N):
+    from oracle.smpl_oracle import SMPLOracle
+    from hierarchicalprobabilistic3dhuman_b200 import synthetic as syn
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    sd = syn.synthetic_state_dict(0)
+    x = torch.from_numpy(syn.synthetic_proxy_rep(ref_batch, seed=0))
+    so = SMPLOracle(syn.synthetic_smpl_model(), torch.float32)
+    parents = syn.SMPL_PARENTS
+    for _ in range(warmup):
+        cpu_reference_step(sd, x, so, N, parents)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(sd, x, so, N, parents)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": ref_batch / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{ref_batch} images x N={N} samples per step, {steps} steps (oracle port of the reference path, torch CPU fp32, {torch.get_num_threads()} threads)"}, dt
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))          # bounded sample: ~1.5-3 s per step on 8+ cores
+    warm = max(1, min(args.warmup, 2))
+    cb, dt = time_cpu_reference(steps, warm, args.ref_batch, args.samples)
+    line = {"metric": "images/sec (B=256, N_samples=100)", "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"1xB200 config: batch 256/GPU, N_samples=100, 18x256x256 proxy rep; reference arm runs a bounded "
+                                   f"sample of {args.ref_batch} images/step on the host cores", "encoder": "ResNet-18",
+                       "smpl": "synthetic SMPL-shaped model (licence-gated file absent)"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- own arm (CUDA)
+def main_hp3d(args):
+    import torch.distributed as dist
+    import hierarchicalprobabilistic3dhuman_b200 as hp
+    from hierarchicalprobabilistic3dhuman_b200 import synthetic as syn, _lib
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, N = args.batch, args.samples
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        dist.barrier()
+
+    net = hp.PoseMFShapeGaussianNet(syn.SMPL_PARENTS.tolist(), cfg(), encoder_mode=args.encoder_mode)
+    net.load_state_dict(syn.synthetic_state_dict(0))
+    net = net.to(dev).eval()
+    smpl = hp.SMPL(model=syn.synthetic_smpl_model()).to(dev)
+    # distinct synthetic images per rank; tile a small pool to the batch size (content does not change the work)
+    pool = torch.from_numpy(syn.synthetic_proxy_rep(16, seed=100 + rank))
+    x_host = pool.repeat((B + 15) // 16, 1, 1, 1)[:B].contiguous().pin_memory()
+    x_dev = x_host.to(dev)
+    torch.manual_seed(1234 + rank)
+
+    # gather buffers: every rank's kernels write straight into its slice (no pack/copy)
+    full = args.gather == "full"
+    g_rot = torch.empty(world * B, N, 23, 3, 3, device=dev)
+    g_betas = torch.empty(world * B, 10, device=dev)
+    g_verts = torch.empty(world * B if full else B, N, 6890, 3, device=dev)
+    g_unc = torch.empty(world * B, 6890, device=dev)
+    sl = slice(rank * B, (rank + 1) * B)
+    vsl = sl if full else slice(0, B)
+    L = _lib.lib()
+    joints = torch.empty(B * N, 90, 3, device=dev)
+    h_smpl = smpl._handle(dev)
+    ws = torch.empty(L.hp3d_smpl_workspace_bytes(h_smpl, B * N, B), dtype=torch.uint8, device=dev)
+
+    def step(x):
+        F, U, S, V, mode, dist_, glob, cam = net(x)
+        glob_R = hp.rot6d_to_rotmat(glob)
+        out_mode = smpl(body_pose=mode, global_orient=glob_R.unsqueeze(1), betas=dist_.loc, pose2rot=False)
+        R = hp.pose_matrix_fisher_sampling_torch(U, S, V, N, out=g_rot[sl])
+        betas = dist_.loc.contiguous()
+        g_betas[sl].copy_(betas)
+        _lib.check(L.hp3d_smpl_forward(h_smpl, betas.data_ptr(), B, glob_R.data_ptr(), B, R.data_ptr(), B * N,
+                                       g_verts[vsl].data_ptr(), joints.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       _lib.stream_ptr()), "hp3d_smpl_forward")
+        _lib.check(L.hp3d_vertex_uncertainty(g_verts[vsl].data_ptr(), B, N, None, g_unc[sl].data_ptr(), _lib.stream_ptr()),
+                   "hp3d_vertex_uncertainty")
+        if world > 1:
+            dist.all_gather_into_tensor(g_rot, g_rot[sl])
+            dist.all_gather_into_tensor(g_betas, g_betas[sl])
+            dist.all_gather_into_tensor(g_unc, g_unc[sl])
+            if full:
+                dist.all_gather_into_tensor(g_verts, g_verts[sl])
+        return out_mode.vertices, joints, R, g_unc[sl]
+
+    launches = 23 + 6 + 1 + 4 + 1 + 4 + 1 + 1   # encoder, head, rot6d, SMPL(mode), sampler, SMPL(samples), stats, betas copy
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            step(x_dev)
+        e1.record()
+        sync_all()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = clk.summary()
+
+    # ---- end to end: pinned host input -> H2D -> step -> D2H of per-image results
+    res_host = [torch.empty(B, 6890, 3).pin_memory(), torch.empty(B * N, 90, 3).pin_memory(),
+                torch.empty(B, N, 23, 3, 3).pin_memory(), torch.empty(B, 6890).pin_memory()]
+
+    def e2e_step():
+        x = x_host.to(dev, non_blocking=True)
+        outs = step(x)
+        for hbuf, o in zip(res_host, outs):
+            hbuf.copy_(o, non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record()
+    sync_all()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+
+    # ---- dominant memory-bound kernel alone: SMPL-LBS (FK + skinning + joints)
+    M = B * N
+    vp = torch.empty(M, 20670, device=dev).normal_()
+    Jt = torch.randn(B, 24, 3, device=dev)
+    gR = hp.rot6d_to_rotmat(torch.randn(B, 6, device=dev))
+    Rr = g_rot[sl].contiguous()
+    for _ in range(3):
+        _lib.check(L.hp3d_smpl_lbs(h_smpl, vp.data_ptr(), Jt.data_ptr(), B, gR.data_ptr(), B, Rr.data_ptr(), M,
+                                   g_verts[vsl].data_ptr(), joints.data_ptr(), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        _lib.check(L.hp3d_smpl_lbs(h_smpl, vp.data_ptr(), Jt.data_ptr(), B, gR.data_ptr(), B, Rr.data_ptr(), M,
+                                   g_verts[vsl].data_ptr(), joints.data_ptr(), _lib.stream_ptr()))
+    e1.record()
+    torch.cuda.synchronize()
+    lbs_ms = e0.elapsed_time(e1) / reps
+    pk, pk_kind = peaks()
+    achieved = LBS_BYTES_PER_MESH * M / (lbs_ms * 1e-3) / 1e9
+
+    # max over ranks
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+    if rank == 0:
+        line = {"metric": "images/sec (B=256, N_samples=100)", "value": world * B / (ms * 1e-3), "unit": "images/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16 (encoder, fp32 accumulate) + f32 (head, sampler, SMPL; blend = 3x fp16-split tensor-core)" if args.encoder_mode == "fast" else "f32",
+                "data": "synthetic",
+                "config": {"workload": f"BASELINE configs[1]/[3] at the metric's batch: {B} images/GPU x N={N} samples, 18x256x256 proxy rep, "
+                                       f"full hot path (encoder+head+sampler+SMPL on {B * N} meshes/GPU)",
+                           "encoder_mode": args.encoder_mode, "gather": args.gather if world > 1 else "none",
+                           "l2": "inputs (1.2 GB/step) and outputs (2.1 GB/step) exceed the 126 MB L2; no explicit flush",
+                           "smpl": "synthetic SMPL-shaped model (licence-gated file absent)", "rng": "in-kernel Philox"},
+                "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s",
+                        "h2d_bytes_per_step": int(x_host.numel() * 4),
+                        "d2h_bytes_per_step": int(sum(h.numel() for h in res_host) * 4),
+                        "d2h": "mode vertices + sampled joints + sampled rotmats + per-vertex uncertainty", "ms_per_step": ms_e2e},
+                "gpu_launches": launches,
+                "clocks": clocks,
+                "roofline": {"kernel": "lbs_kernel (SMPL FK + skinning + 90 joints)", "bound": "hbm", "achieved": achieved,
+                             "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                             "traffic": None, "ms": lbs_ms, "meshes": M, "bytes_per_mesh": LBS_BYTES_PER_MESH}}
+        if not args.no_cpu_baseline and world == 1:
+            cb, _ = time_cpu_reference(2, 1, args.ref_batch, N)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_hp3d(a)

@@ -11,7 +11,7 @@ _lib = None
 EXPORTS = [
     "hp3d_version", "hp3d_last_error",
     "hp3d_smpl_create", "hp3d_smpl_destroy", "hp3d_smpl_workspace_bytes", "hp3d_smpl_forward",
-    "hp3d_smpl_shape_blend", "hp3d_smpl_pose_blend", "hp3d_smpl_lbs", "hp3d_rodrigues", "hp3d_rot6d_to_rotmat",
+    "hp3d_smpl_shape_blend", "hp3d_smpl_pose_blend_workspace_bytes", "hp3d_smpl_pose_blend", "hp3d_smpl_lbs", "hp3d_rodrigues", "hp3d_rot6d_to_rotmat",
     "hp3d_vertex_uncertainty", "hp3d_mf_sample",
     "hp3d_head_create", "hp3d_head_destroy", "hp3d_head_workspace_bytes", "hp3d_head_forward",
     "hp3d_encoder_create", "hp3d_encoder_destroy", "hp3d_encoder_workspace_bytes", "hp3d_encoder_forward", "hp3d_encoder_forward_taps",
@@ -64,7 +64,9 @@ def lib():
     L.hp3d_smpl_forward.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                     c_void_p, c_size_t, c_void_p]
     L.hp3d_smpl_shape_blend.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
-    L.hp3d_smpl_pose_blend.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]
+    L.hp3d_smpl_pose_blend.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
+    L.hp3d_smpl_pose_blend_workspace_bytes.argtypes = [c_int]
+    L.hp3d_smpl_pose_blend_workspace_bytes.restype = c_size_t
     L.hp3d_smpl_lbs.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                 c_void_p, c_void_p]
     L.hp3d_rodrigues.argtypes = [c_void_p, c_int, c_void_p, c_void_p]

@@ -98,7 +98,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int n0 = (mt / (args.tiles_x * args.tiles_y)) * args.BIMG;
         const int ox0 = tx * args.BW, oy0 = ty * args.BH;
         for (int kb = 0; kb < args.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
           uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
@@ -118,11 +118,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < args.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after_sync();
           const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint64_t a_desc = umma_desc_sw128(a_addr);
@@ -157,7 +157,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       float* bsm = bias_s + acc * BN;
       if (et < BN) bsm[et] = args.bias[nt * BN + et];
       asm volatile("bar.sync 1, 128;" ::: "memory");            // epilogue-only named barrier
-      mbar_wait(&tmem_full[acc], acc_phase);
+      mbar_wait(&tmem_full[acc], acc_phase, 4);
       tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1

@@ -1,0 +1,317 @@
+// SMPL pose-corrective blend on the tensor cores (tcgen05 + TMA), sm_100a.
+//
+//   v_posed[m][c] = v_shaped[m / rep][c] + sum_k (R[m][k] - I[k]) * posedirs[k][c]
+//   M = B*N meshes (25,600 at B=256, N=100), K = 207 (padded to 208), C = 20,670      
+//
+// smplx computes this as one fp32 matmul (lbs(): pose_feature @ posedirs). To hold the 1e-4 parity
+// contract on fp16 tensor cores both operands are split into fp16 hi + lo parts and three products
+// are accumulated in fp32 (TMEM):  A_hi B_hi + A_lo B_hi + A_hi B_lo   (error ~2^-22 relative);
+// posedirs are pre-scaled by a power of two so the lo parts stay in fp16's normal range.
+// HP3D_BLEND_PASSES=1 selects the single-product variant (error ~2^-11 of the *offset*, still far
+// below 1e-4 of the vertex scale for SMPL-sized correctives).
+//
+// Kernel anatomy (persistent, warp specialised, one CTA per SM):
+//   work unit = (128-mesh M tile) x (chunk of n tiles); the A tile (pose features, all of K, hi+lo =
+//   128 KB) stays resident in shared memory for the whole unit while 16 KB B tiles (posedirs) stream
+//   through a TMA ring; accumulators are double buffered in TMEM so the epilogue of n-tile i
+//   (TMEM -> registers -> smem transpose -> coalesced fp32 stores, + v_shaped) overlaps the MMAs of i+1.
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <vector>
+#include <algorithm>
+#include <math.h>
+
+using namespace hp3d;
+using namespace hp3d::tc;
+
+namespace {
+
+constexpr int KP = 208;              // padded K (row pitch of the fp16 operands, 416 B)
+constexpr int KBLKS = 4;             // 64-wide k-blocks; the last one holds 16 valid columns
+constexpr int BM = 128, BN = 128;
+constexpr int TILE_BYTES = 128 * 64 * 2;   // 16 KB (A and B tiles alike)
+constexpr int STAGES = 4;
+constexpr int NPAD = 20736;          // 162 * 128
+
+struct BlendArgs {
+  int M, rep;
+  int m_tiles, n_tiles, n_chunk, n_chunks;
+  float inv_scale;
+  const float* v_shaped;   // [Mb][VPITCH]
+  float* v_posed;          // [M][NV3]
+};
+
+template <int PASSES>
+struct BlendSmem {
+  static constexpr int A_TILES = (PASSES == 3) ? 2 * KBLKS : KBLKS;
+  static constexpr int A_OFFSET = 0;
+  static constexpr int B_OFFSET = A_TILES * TILE_BYTES;
+  static constexpr int STG_OFFSET = B_OFFSET + STAGES * TILE_BYTES;     // epilogue transpose staging
+  static constexpr int STG_BYTES = 4 * 32 * 33 * 4;
+  static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(256) pose_feature_split_kernel(const float* __restrict__ body_pose, int M,
+                                                                 __half* __restrict__ hi, __half* __restrict__ lo) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)M * KP) return;
+  const int m = (int)(i / KP), k = (int)(i - (size_t)m * KP);
+  float v = 0.f;
+  if (k < NPF) {
+    const int e = k % 9;
+    v = body_pose[(size_t)m * NPF + k] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+  }
+  const __half h = __float2half_rn(v);
+  hi[i] = h;
+  lo[i] = __float2half_rn(v - __half2float(h));
+}
+
+template <int PASSES>
+__global__ void __launch_bounds__(256, 1)
+blend_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+                const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+                const __grid_constant__ BlendArgs args) {
+  using L = BlendSmem<PASSES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint64_t* a_full = tmem_empty + 2;          // [1]
+  uint64_t* a_empty = a_full + 1;             // [1]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_units = args.m_tiles * args.n_chunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmAhi); tma_prefetch_desc(&tmAlo); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    mbar_init(a_full, 1); mbar_init(a_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<2 * BN>(tmem_base_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0, a_phase = 0;
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const int mt = u / args.n_chunks, chunk = u - mt * args.n_chunks;
+        const int nt0 = chunk * args.n_chunk, nt1 = min(nt0 + args.n_chunk, args.n_tiles);
+        mbar_wait(a_empty, a_phase ^ 1, 5);
+        mbar_arrive_expect_tx(a_full, L::A_TILES * TILE_BYTES);
+        for (int kb = 0; kb < KBLKS; ++kb) {
+          tma_load_2d(smem + L::A_OFFSET + kb * TILE_BYTES, &tmAhi, a_full, kb * 64, mt * BM);
+          if (PASSES == 3) tma_load_2d(smem + L::A_OFFSET + (KBLKS + kb) * TILE_BYTES, &tmAlo, a_full, kb * 64, mt * BM);
+        }
+        a_phase ^= 1;
+        for (int nt = nt0; nt < nt1; ++nt)
+          for (int kb = 0; kb < KBLKS; ++kb)
+            for (int part = 0; part < (PASSES == 3 ? 2 : 1); ++part) {
+              mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+              mbar_arrive_expect_tx(&full_bar[stage], TILE_BYTES);
+              tma_load_2d(smem + L::B_OFFSET + stage * TILE_BYTES, part == 0 ? &tmBhi : &tmBlo, &full_bar[stage], kb * 64, nt * BN);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN);
+      int stage = 0; uint32_t phase = 0, a_phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      const uint32_t a_base = smem_u32(smem + L::A_OFFSET);
+      const uint32_t b_base = smem_u32(smem + L::B_OFFSET);
+      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const int mt = u / args.n_chunks, chunk = u - mt * args.n_chunks;
+        const int nt0 = chunk * args.n_chunk, nt1 = min(nt0 + args.n_chunk, args.n_tiles);
+        mbar_wait(a_full, a_phase, 6);
+        a_phase ^= 1;
+        tc_fence_after_sync();
+        for (int nt = nt0; nt < nt1; ++nt) {
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
+          tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+          for (int kb = 0; kb < KBLKS; ++kb) {
+            const int nmma = (kb < KBLKS - 1) ? 4 : (KP - 64 * (KBLKS - 1)) / 16;   // 4,4,4,1
+            const uint64_t ahi = umma_desc_sw128(a_base + kb * TILE_BYTES);
+            // B_hi[kb]:  A_hi B_hi (+ A_lo B_hi)
+            mbar_wait(&full_bar[stage], phase, 3);
+            tc_fence_after_sync();
+            uint64_t bd = umma_desc_sw128(b_base + stage * TILE_BYTES);
+            for (int k = 0; k < nmma; ++k) umma_f16(d_tmem, ahi + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (PASSES == 3) {
+              const uint64_t alo = umma_desc_sw128(a_base + (KBLKS + kb) * TILE_BYTES);
+              for (int k = 0; k < nmma; ++k) umma_f16(d_tmem, alo + 2 * k, bd + 2 * k, idesc, 1u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (PASSES == 3) {   // B_lo[kb]:  A_hi B_lo
+              mbar_wait(&full_bar[stage], phase, 3);
+              tc_fence_after_sync();
+              bd = umma_desc_sw128(b_base + stage * TILE_BYTES);
+              for (int k = 0; k < nmma; ++k) umma_f16(d_tmem, ahi + 2 * k, bd + 2 * k, idesc, 1u);
+              umma_commit(&empty_bar[stage]);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+          umma_commit(&tmem_full[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        umma_commit(a_empty);     // resident A tile may be overwritten once every MMA of this unit retired
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================================================== epilogue
+    const int ew = warp - 4;
+    float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET) + ew * 32 * 33;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int mt = u / args.n_chunks, chunk = u - mt * args.n_chunks;
+      const int nt0 = chunk * args.n_chunk, nt1 = min(nt0 + args.n_chunk, args.n_tiles);
+      const int m_base = mt * BM + ew * 32;
+      for (int nt = nt0; nt < nt1; ++nt) {
+        mbar_wait(&tmem_full[acc], acc_phase, 4);
+        tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + ch * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = __uint_as_float(r[c]);
+          __syncwarp();
+          const int n = nt * BN + ch * 32 + lane;
+          if (n < NV3) {
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+              const int m = m_base + rr;
+              if (m < args.M) {
+                const float v = stg[rr * 33 + lane] * args.inv_scale + args.v_shaped[(size_t)(m / args.rep) * VPITCH + n];
+                args.v_posed[(size_t)m * NV3 + n] = v;
+              }
+            }
+          }
+          __syncwarp();
+        }
+        tc_fence_before_sync();
+        mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc<2 * BN>(tmem_base); }
+}
+
+struct BlendTc {
+  __half *b_hi = nullptr, *b_lo = nullptr;   // [NPAD][KP]
+  CUtensorMap tmBhi, tmBlo;
+  float inv_scale = 1.f;
+  int num_sms = 148;
+  int passes = 3;
+};
+
+}  // namespace
+
+namespace hp3d {
+
+void blend_tc_destroy(void* p);
+
+int blend_tc_create(const double* posedirs, void** out) {
+  *out = nullptr;
+  if (!encode_fn()) return 0;   // no tensor-map entry point: the fp32 CUDA-core blend is used instead
+  BlendTc* h = new BlendTc();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  const char* e = getenv("HP3D_BLEND_PASSES");
+  h->passes = (e && atoi(e) == 1) ? 1 : 3;
+  double mx = 0.0;
+  for (size_t i = 0; i < (size_t)NPF * NV3; ++i) mx = std::max(mx, fabs(posedirs[i]));
+  int ex = 0;
+  if (mx > 0.0) ex = (int)floor(log2(1024.0 / mx));
+  const double scale = ldexp(1.0, ex);
+  h->inv_scale = (float)ldexp(1.0, -ex);
+  std::vector<__half> bh((size_t)NPAD * KP, __float2half_rn(0.f)), bl((size_t)NPAD * KP, __float2half_rn(0.f));
+  for (int k = 0; k < NPF; ++k)
+    for (int c = 0; c < NV3; ++c) {
+      const float v = (float)(posedirs[(size_t)k * NV3 + c] * scale);
+      const __half hv = __float2half_rn(v);
+      bh[(size_t)c * KP + k] = hv;
+      bl[(size_t)c * KP + k] = __float2half_rn(v - __half2float(hv));
+    }
+  int rc = upload(&h->b_hi, bh.data(), bh.size());
+  rc = rc ? rc : upload(&h->b_lo, bl.data(), bl.size());
+  const uint64_t dims[2] = {KP, NPAD};
+  const uint64_t st[1] = {KP * 2};
+  const uint32_t box[2] = {64, BN};
+  rc = rc ? rc : make_tmap_f16(&h->tmBhi, h->b_hi, 2, dims, st, box);
+  rc = rc ? rc : make_tmap_f16(&h->tmBlo, h->b_lo, 2, dims, st, box);
+  if (rc) { blend_tc_destroy(h); return rc; }
+  *out = h;
+  return 0;
+}
+
+void blend_tc_destroy(void* p) {
+  if (!p) return;
+  BlendTc* h = (BlendTc*)p;
+  cudaFree(h->b_hi); cudaFree(h->b_lo);
+  delete h;
+}
+
+size_t blend_tc_workspace_bytes(int M) {
+  const size_t Mp = (size_t)cdiv(M, BM) * BM;
+  return 2 * align_up(Mp * KP * sizeof(__half), 1024);
+}
+
+int blend_tc_forward(void* p, const float* v_shaped, int Mb, const float* body_pose, int M, float* v_posed,
+                     void* workspace, cudaStream_t stream) {
+  BlendTc* h = (BlendTc*)p;
+  const size_t Mp = (size_t)cdiv(M, BM) * BM;
+  __half* a_hi = (__half*)workspace;
+  __half* a_lo = (__half*)((char*)workspace + align_up(Mp * KP * sizeof(__half), 1024));
+  pose_feature_split_kernel<<<(unsigned)cdiv((int)((size_t)M * KP), 256), 256, 0, stream>>>(body_pose, M, a_hi, a_lo);
+  int rc = launch_status("pose_feature_split_kernel");
+  if (rc) return rc;
+  CUtensorMap tmAhi, tmAlo;
+  const uint64_t dims[2] = {KP, (uint64_t)M};      // rows >= M are out of bounds -> zero filled
+  const uint64_t st[1] = {KP * 2};
+  const uint32_t box[2] = {64, BM};
+  rc = make_tmap_f16(&tmAhi, a_hi, 2, dims, st, box);
+  rc = rc ? rc : make_tmap_f16(&tmAlo, a_lo, 2, dims, st, box);
+  if (rc) return rc;
+  BlendArgs a;
+  a.M = M; a.rep = M / Mb;
+  a.m_tiles = cdiv(M, BM); a.n_tiles = NPAD / BN;
+  a.n_chunk = 18; a.n_chunks = cdiv(a.n_tiles, a.n_chunk);
+  a.inv_scale = h->inv_scale; a.v_shaped = v_shaped; a.v_posed = v_posed;
+  const int grid = std::min(a.m_tiles * a.n_chunks, h->num_sms);
+  if (h->passes == 3) {
+    static bool set = false;
+    if (!set) { HP3D_CUDA(cudaFuncSetAttribute(blend_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, BlendSmem<3>::TOTAL)); set = true; }
+    blend_tc_kernel<3><<<grid, 256, BlendSmem<3>::TOTAL, stream>>>(tmAhi, tmAlo, h->tmBhi, h->tmBlo, a);
+  } else {
+    static bool set = false;
+    if (!set) { HP3D_CUDA(cudaFuncSetAttribute(blend_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BlendSmem<1>::TOTAL)); set = true; }
+    blend_tc_kernel<1><<<grid, 256, BlendSmem<1>::TOTAL, stream>>>(tmAhi, tmAlo, h->tmBhi, h->tmBlo, a);
+  }
+  return launch_status("blend_tc_kernel");
+}
+
+}  // namespace hp3d

@@ -330,8 +330,9 @@ __global__ void __launch_bounds__(256) vertex_uncertainty_kernel(const float* __
 namespace hp3d {
 int blend_tc_create(const double* posedirs, void** out);                      // gemm_tc.cu
 void blend_tc_destroy(void* p);
+size_t blend_tc_workspace_bytes(int M);
 int blend_tc_forward(void* p, const float* v_shaped, int Mb, const float* body_pose, int M, float* v_posed,
-                     cudaStream_t stream);
+                     void* workspace, cudaStream_t stream);
 }
 
 extern "C" int hp3d_smpl_create(const hp3d_smpl_model* md, hp3d_smpl** out) {
@@ -430,9 +431,11 @@ static size_t ws_vshaped(int Mb) { return align_up((size_t)Mb * VPITCH * sizeof(
 static size_t ws_J(int Mb) { return align_up((size_t)Mb * NJ * 3 * sizeof(float), 256); }
 static size_t ws_vposed(int M) { return align_up((size_t)M * NV3 * sizeof(float), 256); }
 
+extern "C" size_t hp3d_smpl_pose_blend_workspace_bytes(int M) { return M > 0 ? blend_tc_workspace_bytes(M) : 0; }
+
 extern "C" size_t hp3d_smpl_workspace_bytes(const hp3d_smpl*, int M, int Mb) {
   if (M <= 0 || Mb <= 0) return 0;
-  return ws_vshaped(Mb) + ws_J(Mb) + ws_vposed(M);
+  return ws_vshaped(Mb) + ws_J(Mb) + ws_vposed(M) + blend_tc_workspace_bytes(M);
 }
 
 extern "C" int hp3d_smpl_shape_blend(const hp3d_smpl* h, const float* betas, int Mb, float* v_shaped, float* J,
@@ -454,10 +457,12 @@ static int blend_mode() {
 }
 
 extern "C" int hp3d_smpl_pose_blend(const hp3d_smpl* h, const float* v_shaped, int Mb, const float* body_pose, int M,
-                                    float* v_posed, void* stream) {
+                                    float* v_posed, void* workspace, size_t workspace_bytes, void* stream) {
   HP3D_ARG(h && v_shaped && body_pose && v_posed && M > 0 && Mb > 0 && M % Mb == 0, "bad argument");
-  if (blend_mode() == 1 && h->blend_tc)
-    return blend_tc_forward(h->blend_tc, v_shaped, Mb, body_pose, M, v_posed, (cudaStream_t)stream);
+  if (blend_mode() == 1 && h->blend_tc) {
+    HP3D_ARG(workspace && workspace_bytes >= blend_tc_workspace_bytes(M), "workspace too small (hp3d_smpl_pose_blend_workspace_bytes)");
+    return blend_tc_forward(h->blend_tc, v_shaped, Mb, body_pose, M, v_posed, workspace, (cudaStream_t)stream);
+  }
   dim3 grid(cdiv(NV3, PB_BN), cdiv(M, PB_BM));
   pose_blend_fp32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(body_pose, h->posedirs, v_shaped, M, M / Mb, v_posed);
   return launch_status("pose_blend_fp32_kernel");
@@ -484,10 +489,10 @@ extern "C" int hp3d_smpl_forward(const hp3d_smpl* h, const float* betas, int Mb,
   char* ws = (char*)workspace;
   float* v_shaped = (float*)ws; ws += ws_vshaped(Mb);
   float* J = (float*)ws; ws += ws_J(Mb);
-  float* v_posed = (float*)ws;
+  float* v_posed = (float*)ws; ws += ws_vposed(M);
   int rc = hp3d_smpl_shape_blend(h, betas, Mb, v_shaped, J, stream);
   if (rc) return rc;
-  rc = hp3d_smpl_pose_blend(h, v_shaped, Mb, body_pose, M, v_posed, stream);
+  rc = hp3d_smpl_pose_blend(h, v_shaped, Mb, body_pose, M, v_posed, ws, blend_tc_workspace_bytes(M), stream);
   if (rc) return rc;
   return hp3d_smpl_lbs(h, v_posed, J, Mb, global_orient, Mg, body_pose, M, vertices, joints, stream);
 }

@@ -36,8 +36,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
+// Bounded wait: a protocol bug (wrong parity / byte count / missing commit) must surface as a trapped
+// kernel with a message, never as a hung GPU.
+static __device__ __noinline__ void mbar_timeout(int tag, uint32_t parity) {
+  printf("libhp3d: mbarrier wait timed out (tag %d, parity %u, block %d, thread %d)\n", tag, parity, (int)blockIdx.x, (int)threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) mbar_timeout(tag, parity);   // ~2 s
+  }
 }
 
 // ---------------------------------------------------------------- TMA loads (tile mode, mbarrier completion)

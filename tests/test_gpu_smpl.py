@@ -49,7 +49,8 @@ def test_stage_outputs_match_oracle(setup):
     vs = torch.empty(M, 20672, device="cuda"); J = torch.empty(M, 24, 3, device="cuda"); vp = torch.empty(M, 20670, device="cuda")
     b, p = betas.cuda(), pose.cuda().contiguous()
     _lib.check(L.hp3d_smpl_shape_blend(h, b.data_ptr(), M, vs.data_ptr(), J.data_ptr(), None))
-    _lib.check(L.hp3d_smpl_pose_blend(h, vs.data_ptr(), M, p.data_ptr(), M, vp.data_ptr(), None))
+    wsb = torch.empty(L.hp3d_smpl_pose_blend_workspace_bytes(M), dtype=torch.uint8, device="cuda")
+    _lib.check(L.hp3d_smpl_pose_blend(h, vs.data_ptr(), M, p.data_ptr(), M, vp.data_ptr(), wsb.data_ptr(), wsb.numel(), None))
     torch.cuda.synchronize()
     assert rel_err(vs[:, :20670].reshape(M, 6890, 3), ref["v_shaped"]) < 1e-6
     assert rel_err(J, ref["J"]) < 1e-5
