@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--encoder-mode", default="fast", choices=["fast", "parity"])
     ap.add_argument("--ref-batch", type=int, default=4, help="images per step of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="one warm-up + the timed steps only (for ncu): no e2e / LBS-alone / CPU legs")
+    ap.add_argument("--ref-threads", type=int, default=0, help="torch CPU threads for the reference arm (0 = pick the best of a sweep)")
     ap.add_argument("--gather", default="full", choices=["full", "stats"],
                     help="N>1: all-gather (rotmats, betas, vertices) [configs[3]] or per-image statistics only")
     return ap.parse_args()
@@ -193,32 +195,24 @@ def main_hp3d(args):
     g_unc = torch.empty(world * B, 6890, device=dev)
     sl = slice(rank * B, (rank + 1) * B)
     vsl = sl if full else slice(0, B)
+    pipe = hp.HotPathPipeline(net, smpl, B, N, dev, rotmats_out=g_rot[sl], betas_out=g_betas[sl],
+                              vertices_out=g_verts[vsl], uncertainty_out=g_unc[sl])
     L = _lib.lib()
-    joints = torch.empty(B * N, 90, 3, device=dev)
-    h_smpl = smpl._handle(dev)
-    ws = torch.empty(L.hp3d_smpl_workspace_bytes(h_smpl, B * N, B), dtype=torch.uint8, device=dev)
+    h_smpl, joints = pipe.h_smpl, pipe.joints
 
-    def step(x):
-        F, U, S, V, mode, dist_, glob, cam = net(x)
-        glob_R = hp.rot6d_to_rotmat(glob)
-        out_mode = smpl(body_pose=mode, global_orient=glob_R.unsqueeze(1), betas=dist_.loc, pose2rot=False)
-        R = hp.pose_matrix_fisher_sampling_torch(U, S, V, N, out=g_rot[sl])
-        betas = dist_.loc.contiguous()
-        g_betas[sl].copy_(betas)
-        _lib.check(L.hp3d_smpl_forward(h_smpl, betas.data_ptr(), B, glob_R.data_ptr(), B, R.data_ptr(), B * N,
-                                       g_verts[vsl].data_ptr(), joints.data_ptr(), ws.data_ptr(), ws.numel(),
-                                       _lib.stream_ptr()), "hp3d_smpl_forward")
-        _lib.check(L.hp3d_vertex_uncertainty(g_verts[vsl].data_ptr(), B, N, None, g_unc[sl].data_ptr(), _lib.stream_ptr()),
-                   "hp3d_vertex_uncertainty")
+    def gather():
         if world > 1:
             dist.all_gather_into_tensor(g_rot, g_rot[sl])
             dist.all_gather_into_tensor(g_betas, g_betas[sl])
             dist.all_gather_into_tensor(g_unc, g_unc[sl])
             if full:
                 dist.all_gather_into_tensor(g_verts, g_verts[sl])
-        return out_mode.vertices, joints, R, g_unc[sl]
 
-    launches = 23 + 6 + 1 + 4 + 1 + 4 + 1 + 1   # encoder, head, rot6d, SMPL(mode), sampler, SMPL(samples), stats, betas copy
+    def step(x):
+        pipe.run_device(x)
+        gather()
+
+    launches = pipe.launches_per_pass
 
     def sync_all():
         torch.cuda.synchronize()
@@ -227,7 +221,7 @@ def main_hp3d(args):
             torch.cuda.synchronize()
 
     # ---- device-resident timing
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(1 if args.profile else max(args.warmup, 3)):
         step(x_dev)
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -239,25 +233,29 @@ def main_hp3d(args):
         sync_all()
     ms = e0.elapsed_time(e1) / args.steps
     clocks = clk.summary()
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_ms_per_step": ms}))
+        return
 
-    # ---- end to end: pinned host input -> H2D -> step -> D2H of per-image results
-    res_host = [torch.empty(B, 6890, 3).pin_memory(), torch.empty(B * N, 90, 3).pin_memory(),
-                torch.empty(B, N, 23, 3, 3).pin_memory(), torch.empty(B, 6890).pin_memory()]
-
-    def e2e_step():
-        x = x_host.to(dev, non_blocking=True)
-        outs = step(x)
-        for hbuf, o in zip(res_host, outs):
-            hbuf.copy_(o, non_blocking=True)
-    for _ in range(2):
-        e2e_step()
+    # ---- end to end through the public API: pinned host input -> chunked H2D overlapped with the encoder ->
+    #      hot path -> D2H of the per-image results; every step copies its own input and reads its own results
+    x_hosts = [x_host, x_host.clone().pin_memory()]
+    last = None
+    for i in range(2):
+        last = pipe.run_host(x_hosts[i & 1])
+        gather()
+    last[1].synchronize()
     sync_all()
     e0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    for i in range(args.steps):
+        last = pipe.run_host(x_hosts[i & 1])
+        gather()
+    last[1].synchronize()
     e1.record()
     sync_all()
     ms_e2e = e0.elapsed_time(e1) / args.steps
+    d2h_bytes = pipe.d2h_bytes()
 
     # ---- dominant memory-bound kernel alone: SMPL-LBS (FK + skinning + joints)
     M = B * N
@@ -298,8 +296,9 @@ def main_hp3d(args):
                            "smpl": "synthetic SMPL-shaped model (licence-gated file absent)", "rng": "in-kernel Philox"},
                 "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s",
                         "h2d_bytes_per_step": int(x_host.numel() * 4),
-                        "d2h_bytes_per_step": int(sum(h.numel() for h in res_host) * 4),
-                        "d2h": "mode vertices + sampled joints + sampled rotmats + per-vertex uncertainty", "ms_per_step": ms_e2e},
+                        "d2h_bytes_per_step": int(d2h_bytes),
+                        "d2h": "mode vertices + sampled joints + sampled rotmats + per-vertex uncertainty",
+                        "overlap": "4-chunk H2D on a copy stream overlapped with the encoder; consecutive steps double-buffered", "ms_per_step": ms_e2e},
                 "gpu_launches": launches,
                 "clocks": clocks,
                 "roofline": {"kernel": "lbs_kernel (SMPL FK + skinning + 90 joints)", "bound": "hbm", "achieved": achieved,

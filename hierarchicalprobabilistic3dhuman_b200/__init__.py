@@ -14,7 +14,8 @@ from .smpl import SMPL, SMPLOutput
 from .sampling import (pose_matrix_fisher_sampling_torch, compute_vertex_uncertainties_by_poseMF_shapeGaussian_sampling,
                        sample_meshes_batched, vertex_uncertainty)
 from .rigid import rot6d_to_rotmat
+from .pipeline import HotPathPipeline
 
 __all__ = ["PoseMFShapeGaussianNet", "SMPL", "SMPLOutput", "pose_matrix_fisher_sampling_torch",
            "compute_vertex_uncertainties_by_poseMF_shapeGaussian_sampling", "sample_meshes_batched",
-           "vertex_uncertainty", "rot6d_to_rotmat"]
+           "vertex_uncertainty", "rot6d_to_rotmat", "HotPathPipeline"]

@@ -64,7 +64,7 @@ def lib():
     L.hp3d_smpl_forward.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                     c_void_p, c_size_t, c_void_p]
     L.hp3d_smpl_shape_blend.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
-    L.hp3d_smpl_pose_blend.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
+    L.hp3d_smpl_pose_blend.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
     L.hp3d_smpl_pose_blend_workspace_bytes.argtypes = [c_int]
     L.hp3d_smpl_pose_blend_workspace_bytes.restype = c_size_t
     L.hp3d_smpl_lbs.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,

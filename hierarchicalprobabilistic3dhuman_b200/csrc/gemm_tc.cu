@@ -1,7 +1,10 @@
 // SMPL pose-corrective blend on the tensor cores (tcgen05 + TMA), sm_100a.
 //
-//   v_posed[m][c] = v_shaped[m / rep][c] + sum_k (R[m][k] - I[k]) * posedirs[k][c]
-//   M = B*N meshes (25,600 at B=256, N=100), K = 207 (padded to 208), C = 20,670      
+//   v_posed[m][c] = v_template[c] + sum_l beta[m/rep][l] shapedirs[c][l] + sum_k (R[m][k] - I[k]) posedirs[k][c]
+//   M = B*N meshes (25,600 at B=256, N=100), C = 20,670                                 
+// i.e. ONE GEMM with K = 207 pose features + 10 betas + 1 (template) = 218 (padded to 224):
+//   A'[m] = [R[m]-I | beta[m/rep] | 1],  B'[c] = [posedirs[:,c] | shapedirs[c,:] | v_template[c]]
+// so the shape blend rides along and the epilogue is a pure scaled store.
 //
 // smplx computes this as one fp32 matmul (lbs(): pose_feature @ posedirs). To hold the 1e-4 parity
 // contract on fp16 tensor cores both operands are split into fp16 hi + lo parts and three products
@@ -26,8 +29,8 @@ using namespace hp3d::tc;
 
 namespace {
 
-constexpr int KP = 208;              // padded K (row pitch of the fp16 operands, 416 B)
-constexpr int KBLKS = 4;             // 64-wide k-blocks; the last one holds 16 valid columns
+constexpr int KP = 224;              // padded K = 207 + 10 + 1 -> 224 (row pitch of the fp16 operands, 448 B)
+constexpr int KBLKS = 4;             // 64-wide k-blocks; the last one holds 32 valid columns
 constexpr int BM = 128, BN = 128;
 constexpr int TILE_BYTES = 128 * 64 * 2;   // 16 KB (A and B tiles alike)
 constexpr int STAGES = 4;
@@ -37,7 +40,6 @@ struct BlendArgs {
   int M, rep;
   int m_tiles, n_tiles, n_chunk, n_chunks;
   float inv_scale;
-  const float* v_shaped;   // [Mb][VPITCH]
   float* v_posed;          // [M][NV3]
 };
 
@@ -52,7 +54,8 @@ struct BlendSmem {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
-__global__ void __launch_bounds__(256) pose_feature_split_kernel(const float* __restrict__ body_pose, int M,
+__global__ void __launch_bounds__(256) pose_feature_split_kernel(const float* __restrict__ body_pose,
+                                                                 const float* __restrict__ betas, int rep, int M,
                                                                  __half* __restrict__ hi, __half* __restrict__ lo) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)M * KP) return;
@@ -61,6 +64,10 @@ __global__ void __launch_bounds__(256) pose_feature_split_kernel(const float* __
   if (k < NPF) {
     const int e = k % 9;
     v = body_pose[(size_t)m * NPF + k] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
+  } else if (k < NPF + NBETA) {
+    v = betas[(size_t)(m / rep) * NBETA + (k - NPF)];
+  } else if (k == NPF + NBETA) {
+    v = 1.f;
   }
   const __half h = __float2half_rn(v);
   hi[i] = h;
@@ -197,14 +204,11 @@ blend_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
           __syncwarp();
           const int n = nt * BN + ch * 32 + lane;
           if (n < NV3) {
-#pragma unroll 4
-            for (int rr = 0; rr < 32; ++rr) {
-              const int m = m_base + rr;
-              if (m < args.M) {
-                const float v = stg[rr * 33 + lane] * args.inv_scale + args.v_shaped[(size_t)(m / args.rep) * VPITCH + n];
-                args.v_posed[(size_t)m * NV3 + n] = v;
-              }
-            }
+            float* dst = args.v_posed + (size_t)m_base * NV3 + n;
+            const int rows = min(32, args.M - m_base);
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr)
+              if (rr < rows) dst[(size_t)rr * NV3] = stg[rr * 33 + lane] * args.inv_scale;
           }
           __syncwarp();
         }
@@ -233,7 +237,7 @@ namespace hp3d {
 
 void blend_tc_destroy(void* p);
 
-int blend_tc_create(const double* posedirs, void** out) {
+int blend_tc_create(const double* posedirs, const double* shapedirs, const double* v_template, void** out) {
   *out = nullptr;
   if (!encode_fn()) return 0;   // no tensor-map entry point: the fp32 CUDA-core blend is used instead
   BlendTc* h = new BlendTc();
@@ -244,17 +248,21 @@ int blend_tc_create(const double* posedirs, void** out) {
   h->passes = (e && atoi(e) == 1) ? 1 : 3;
   double mx = 0.0;
   for (size_t i = 0; i < (size_t)NPF * NV3; ++i) mx = std::max(mx, fabs(posedirs[i]));
+  for (size_t i = 0; i < (size_t)NV3 * NBETA; ++i) mx = std::max(mx, fabs(shapedirs[i]));
+  for (size_t i = 0; i < (size_t)NV3; ++i) mx = std::max(mx, fabs(v_template[i]));
   int ex = 0;
-  if (mx > 0.0) ex = (int)floor(log2(1024.0 / mx));
+  if (mx > 0.0) ex = (int)floor(log2(16384.0 / mx));
   const double scale = ldexp(1.0, ex);
   h->inv_scale = (float)ldexp(1.0, -ex);
   std::vector<__half> bh((size_t)NPAD * KP, __float2half_rn(0.f)), bl((size_t)NPAD * KP, __float2half_rn(0.f));
-  for (int k = 0; k < NPF; ++k)
-    for (int c = 0; c < NV3; ++c) {
-      const float v = (float)(posedirs[(size_t)k * NV3 + c] * scale);
+  for (int c = 0; c < NV3; ++c)
+    for (int k = 0; k < NPF + NBETA + 1; ++k) {
+      const double d = (k < NPF) ? posedirs[(size_t)k * NV3 + c]
+                     : (k < NPF + NBETA) ? shapedirs[(size_t)c * NBETA + (k - NPF)] : v_template[c];
+      const float v = (float)(d * scale);
       const __half hv = __float2half_rn(v);
       bh[(size_t)c * KP + k] = hv;
-      bl[(size_t)c * KP + k] = __float2half_rn(v - __half2float(hv));
+      bl[(size_t)c * KP + k] = __float2half_rn((float)(d * scale - (double)__half2float(hv)));
     }
   int rc = upload(&h->b_hi, bh.data(), bh.size());
   rc = rc ? rc : upload(&h->b_lo, bl.data(), bl.size());
@@ -280,13 +288,13 @@ size_t blend_tc_workspace_bytes(int M) {
   return 2 * align_up(Mp * KP * sizeof(__half), 1024);
 }
 
-int blend_tc_forward(void* p, const float* v_shaped, int Mb, const float* body_pose, int M, float* v_posed,
+int blend_tc_forward(void* p, const float* betas, int Mb, const float* body_pose, int M, float* v_posed,
                      void* workspace, cudaStream_t stream) {
   BlendTc* h = (BlendTc*)p;
   const size_t Mp = (size_t)cdiv(M, BM) * BM;
   __half* a_hi = (__half*)workspace;
   __half* a_lo = (__half*)((char*)workspace + align_up(Mp * KP * sizeof(__half), 1024));
-  pose_feature_split_kernel<<<(unsigned)cdiv((int)((size_t)M * KP), 256), 256, 0, stream>>>(body_pose, M, a_hi, a_lo);
+  pose_feature_split_kernel<<<(unsigned)(((size_t)M * KP + 255) / 256), 256, 0, stream>>>(body_pose, betas, M / Mb, M, a_hi, a_lo);
   int rc = launch_status("pose_feature_split_kernel");
   if (rc) return rc;
   CUtensorMap tmAhi, tmAlo;
@@ -300,7 +308,7 @@ int blend_tc_forward(void* p, const float* v_shaped, int Mb, const float* body_p
   a.M = M; a.rep = M / Mb;
   a.m_tiles = cdiv(M, BM); a.n_tiles = NPAD / BN;
   a.n_chunk = 18; a.n_chunks = cdiv(a.n_tiles, a.n_chunk);
-  a.inv_scale = h->inv_scale; a.v_shaped = v_shaped; a.v_posed = v_posed;
+  a.inv_scale = h->inv_scale; a.v_posed = v_posed;
   const int grid = std::min(a.m_tiles * a.n_chunks, h->num_sms);
   if (h->passes == 3) {
     static bool set = false;

@@ -39,6 +39,11 @@ struct hp3d_smpl {
   int* pick_ids = nullptr;       // [NPICK]
   SmplTree tree;
   void* blend_tc = nullptr;      // tensor-core pose-blend operands (gemm_tc.cu), optional
+  // tile-local skinning tables (64-vertex tiles): distinct joints of the tile + dense per-vertex weights
+  int tile_nq_max = 0;           // 0 => tables unavailable (some tile touches > 12 joints): generic kernel
+  int* tile_nq = nullptr;        // [NT]
+  int* tile_joff = nullptr;      // [NT][12]  joint * 3 (float4 units inside one mesh's A block)
+  float* tile_w = nullptr;       // [NT][12][64]
 };
 
 // ------------------------------------------------------------------ shape blend (K=10, fp32 FFMA)
@@ -258,6 +263,165 @@ __global__ void __launch_bounds__(256) lbs_kernel(const float* __restrict__ v_po
   }
 }
 
+// ------------------------------------------------------------------ fused FK + LBS + joints, tile-local variant
+// The generic kernel above is bound by shared-memory wavefronts: every vertex gathers 4 x 48 B of A
+// with lane-varying addresses (12 LDS.128 = 48 wavefronts per 32 vertices, vs ~33 cycles of HBM time).
+// Skinning weights are spatially coherent (a run of consecutive vertices touches a handful of joints),
+// so at create time each 64-vertex tile gets the list of joints it touches (nq <= 12) and dense
+// per-vertex weights over that list. Then A_{joint q} is a WARP-UNIFORM shared-memory address (broadcast,
+// one wavefront per LDS.128), weights/indices live in registers across the G meshes a CTA owns, and the
+// vertex stream is moved with 8-byte vector loads/stores (2 vertices = 24 B per lane; 82,680 B mesh rows
+// are 8-byte aligned for every mesh). One CTA = G consecutive meshes: warp g runs the FK of mesh g, then
+// the 8 warps sweep the 108 tiles x G meshes, then 66 x G threads-worth of joint regression.
+constexpr int TV = 64;                      // vertices per tile
+constexpr int NT = (NV + TV - 1) / TV;      // 108
+constexpr int NQCAP = 12;
+constexpr int LBS_G = 8;                    // meshes per CTA (== warps per CTA)
+
+template <int NQMAX>
+__global__ void __launch_bounds__(256, 2) lbs_tile_kernel(const float* __restrict__ v_posed, const float* __restrict__ J,
+                                                          int Mb, const float* __restrict__ global_orient, int Mg,
+                                                          const float* __restrict__ body_pose, int M,
+                                                          const int* __restrict__ tile_nq, const int* __restrict__ tile_joff,
+                                                          const float* __restrict__ tile_w,
+                                                          const int* __restrict__ reg_rowptr, const int* __restrict__ reg_col,
+                                                          const float* __restrict__ reg_val, const int* __restrict__ pick_ids,
+                                                          SmplTree tree, float* __restrict__ vertices,
+                                                          float* __restrict__ joints) {
+  __shared__ float4 sA[LBS_G][NJ * 3];
+  __shared__ float sG[LBS_G][NJ][12];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int repb = M / Mb, repg = M / Mg;
+  const int m0 = blockIdx.x * LBS_G;
+  const int Gv = min(LBS_G, M - m0);
+  // ---- phase 1: forward kinematics, warp g <-> mesh m0 + g
+  if (warp < Gv) {
+    const int m = m0 + warp, j = lane;
+    float R[9], Jj[3] = {0.f, 0.f, 0.f}, rel[3] = {0.f, 0.f, 0.f};
+    int par = -1, dep = 99;
+    if (j < NJ) {
+      const float* src = (j == 0) ? (global_orient + (size_t)(m / repg) * 9) : (body_pose + ((size_t)m * NBJ + (j - 1)) * 9);
+#pragma unroll
+      for (int e = 0; e < 9; ++e) R[e] = src[e];
+      const float* Jm = J + (size_t)(m / repb) * NJ * 3;
+      par = tree.parent[j]; dep = tree.depth[j];
+#pragma unroll
+      for (int e = 0; e < 3; ++e) { Jj[e] = Jm[j * 3 + e]; rel[e] = (par >= 0) ? (Jj[e] - Jm[par * 3 + e]) : Jj[e]; }
+    }
+    float G[12];
+    for (int d = 0; d <= tree.max_depth; ++d) {
+      if (dep == d) {
+        if (par < 0) {
+#pragma unroll
+          for (int e = 0; e < 9; ++e) G[e] = R[e];
+          G[9] = rel[0]; G[10] = rel[1]; G[11] = rel[2];
+        } else {
+          float P[12];
+#pragma unroll
+          for (int e = 0; e < 12; ++e) P[e] = sG[warp][par][e];
+          mat3_mul(P, R, G);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+            G[9 + i] = fmaf(P[i * 3 + 2], rel[2], fmaf(P[i * 3 + 1], rel[1], P[i * 3] * rel[0])) + P[9 + i];
+        }
+#pragma unroll
+        for (int e = 0; e < 12; ++e) sG[warp][j][e] = G[e];
+      }
+      __syncwarp();
+    }
+    if (j < NJ) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const float t = G[9 + i] - fmaf(G[i * 3 + 2], Jj[2], fmaf(G[i * 3 + 1], Jj[1], G[i * 3] * Jj[0]));
+        sA[warp][j * 3 + i] = make_float4(G[i * 3], G[i * 3 + 1], G[i * 3 + 2], t);
+      }
+      if (joints) {
+        float* jo = joints + ((size_t)m * NOUTJ + j) * 3;
+        jo[0] = G[9]; jo[1] = G[10]; jo[2] = G[11];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: skinning, warp sweeps tiles, meshes innermost (weights stay in registers)
+  for (int tile = warp; tile < NT; tile += 8) {
+    const int nq = tile_nq[tile];
+    const int v0 = tile * TV + 2 * lane;
+    const bool valid = v0 < NV;                       // NV is even: a lane's two vertices are both in or out
+    float w0[NQMAX], w1[NQMAX];
+    int joff[NQMAX];
+#pragma unroll
+    for (int q = 0; q < NQMAX; ++q) {
+      w0[q] = 0.f; w1[q] = 0.f; joff[q] = 0;
+      if (q < nq) {
+        const float2 w = *reinterpret_cast<const float2*>(tile_w + ((size_t)tile * NQCAP + q) * TV + 2 * lane);
+        w0[q] = w.x; w1[q] = w.y;
+        joff[q] = tile_joff[tile * NQCAP + q];
+      }
+    }
+    const size_t voff = (size_t)3 * v0;
+#pragma unroll 2
+    for (int g = 0; g < Gv; ++g) {
+      const float* src = v_posed + (size_t)(m0 + g) * NV3 + voff;
+      float2 p0 = make_float2(0.f, 0.f), p1 = p0, p2 = p0;
+      if (valid) {
+        p0 = *reinterpret_cast<const float2*>(src);
+        p1 = *reinterpret_cast<const float2*>(src + 2);
+        p2 = *reinterpret_cast<const float2*>(src + 4);
+      }
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, b0 = a0, b1 = a0, b2 = a0;
+      const float4* Ag = sA[g];
+#pragma unroll
+      for (int q = 0; q < NQMAX; ++q) {
+        if (q < nq) {
+          const float4 r0 = Ag[joff[q]], r1 = Ag[joff[q] + 1], r2 = Ag[joff[q] + 2];
+          const float u = w0[q], v = w1[q];
+          a0.x = fmaf(u, r0.x, a0.x); a0.y = fmaf(u, r0.y, a0.y); a0.z = fmaf(u, r0.z, a0.z); a0.w = fmaf(u, r0.w, a0.w);
+          a1.x = fmaf(u, r1.x, a1.x); a1.y = fmaf(u, r1.y, a1.y); a1.z = fmaf(u, r1.z, a1.z); a1.w = fmaf(u, r1.w, a1.w);
+          a2.x = fmaf(u, r2.x, a2.x); a2.y = fmaf(u, r2.y, a2.y); a2.z = fmaf(u, r2.z, a2.z); a2.w = fmaf(u, r2.w, a2.w);
+          b0.x = fmaf(v, r0.x, b0.x); b0.y = fmaf(v, r0.y, b0.y); b0.z = fmaf(v, r0.z, b0.z); b0.w = fmaf(v, r0.w, b0.w);
+          b1.x = fmaf(v, r1.x, b1.x); b1.y = fmaf(v, r1.y, b1.y); b1.z = fmaf(v, r1.z, b1.z); b1.w = fmaf(v, r1.w, b1.w);
+          b2.x = fmaf(v, r2.x, b2.x); b2.y = fmaf(v, r2.y, b2.y); b2.z = fmaf(v, r2.z, b2.z); b2.w = fmaf(v, r2.w, b2.w);
+        }
+      }
+      if (valid) {
+        const float x0 = p0.x, y0 = p0.y, z0 = p1.x, x1 = p1.y, y1 = p2.x, z1 = p2.y;
+        float2 o0, o1, o2;
+        o0.x = fmaf(a0.z, z0, fmaf(a0.y, y0, a0.x * x0)) + a0.w;
+        o0.y = fmaf(a1.z, z0, fmaf(a1.y, y0, a1.x * x0)) + a1.w;
+        o1.x = fmaf(a2.z, z0, fmaf(a2.y, y0, a2.x * x0)) + a2.w;
+        o1.y = fmaf(b0.z, z1, fmaf(b0.y, y1, b0.x * x1)) + b0.w;
+        o2.x = fmaf(b1.z, z1, fmaf(b1.y, y1, b1.x * x1)) + b1.w;
+        o2.y = fmaf(b2.z, z1, fmaf(b2.y, y1, b2.x * x1)) + b2.w;
+        float* dst = vertices + (size_t)(m0 + g) * NV3 + voff;
+        *reinterpret_cast<float2*>(dst) = o0;
+        *reinterpret_cast<float2*>(dst + 2) = o1;
+        *reinterpret_cast<float2*>(dst + 4) = o2;
+      }
+    }
+  }
+  if (!joints) return;
+  __syncthreads();
+  // ---- phase 3: picked + regressed joints of the G meshes (vertices re-read through L2)
+  for (int it = tid; it < Gv * (NPICK + NREG); it += 256) {
+    const int g = it / (NPICK + NREG), r = it - g * (NPICK + NREG);
+    const float* vo = vertices + (size_t)(m0 + g) * NV3;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    if (r < NPICK) {
+      const int v = pick_ids[r];
+      ax = __ldcg(vo + 3 * v); ay = __ldcg(vo + 3 * v + 1); az = __ldcg(vo + 3 * v + 2);
+    } else {
+      const int rr = r - NPICK;
+      for (int p = reg_rowptr[rr]; p < reg_rowptr[rr + 1]; ++p) {
+        const int v = reg_col[p];
+        const float w = reg_val[p];
+        ax = fmaf(w, __ldcg(vo + 3 * v), ax); ay = fmaf(w, __ldcg(vo + 3 * v + 1), ay); az = fmaf(w, __ldcg(vo + 3 * v + 2), az);
+      }
+    }
+    float* jo = joints + ((size_t)(m0 + g) * NOUTJ + NJ + r) * 3;
+    jo[0] = ax; jo[1] = ay; jo[2] = az;
+  }
+}
+
 // ------------------------------------------------------------------ small rotation kernels
 __global__ void rodrigues_kernel(const float* __restrict__ aa, int n, float* __restrict__ R) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -328,10 +492,10 @@ __global__ void __launch_bounds__(256) vertex_uncertainty_kernel(const float* __
 
 // ------------------------------------------------------------------ host side
 namespace hp3d {
-int blend_tc_create(const double* posedirs, void** out);                      // gemm_tc.cu
+int blend_tc_create(const double* posedirs, const double* shapedirs, const double* v_template, void** out);   // gemm_tc.cu
 void blend_tc_destroy(void* p);
 size_t blend_tc_workspace_bytes(int M);
-int blend_tc_forward(void* p, const float* v_shaped, int Mb, const float* body_pose, int M, float* v_posed,
+int blend_tc_forward(void* p, const float* betas, int Mb, const float* body_pose, int M, float* v_posed,
                      void* workspace, cudaStream_t stream);
 }
 
@@ -389,6 +553,31 @@ extern "C" int hp3d_smpl_create(const hp3d_smpl_model* md, hp3d_smpl** out) {
     for (; c < K; ++c) sidx[(size_t)c * NV + v] = sidx[v];   // zero weight, benign index
   }
   h->skin_k = K;
+  // tile-local tables
+  std::vector<int> tnq(NT, 0), tjoff((size_t)NT * NQCAP, 0);
+  std::vector<float> tw((size_t)NT * NQCAP * TV, 0.f);
+  int nq_max = 0;
+  bool tiles_ok = true;
+  for (int t = 0; t < NT && tiles_ok; ++t) {
+    int slot[NJ];
+    for (int j = 0; j < NJ; ++j) slot[j] = -1;
+    int nq = 0;
+    for (int v = t * TV; v < std::min(NV, (t + 1) * TV); ++v)
+      for (int j = 0; j < NJ; ++j)
+        if (md->lbs_weights[(size_t)v * NJ + j] != 0.0 && slot[j] < 0) slot[j] = nq++;
+    if (nq > NQCAP) { tiles_ok = false; break; }
+    // renumber in joint order so the table is deterministic
+    int q = 0;
+    for (int j = 0; j < NJ; ++j) if (slot[j] >= 0) { slot[j] = q; tjoff[(size_t)t * NQCAP + q] = j * 3; ++q; }
+    for (int v = t * TV; v < std::min(NV, (t + 1) * TV); ++v)
+      for (int j = 0; j < NJ; ++j) {
+        const double w = md->lbs_weights[(size_t)v * NJ + j];
+        if (w != 0.0) tw[((size_t)t * NQCAP + slot[j]) * TV + (v - t * TV)] = (float)w;
+      }
+    tnq[t] = nq;
+    nq_max = std::max(nq_max, nq);
+  }
+  h->tile_nq_max = tiles_ok ? nq_max : 0;
   std::vector<int> rp(NREG + 1, 0), rcol;
   std::vector<float> rval;
   for (int r = 0; r < NREG; ++r) {
@@ -412,7 +601,10 @@ extern "C" int hp3d_smpl_create(const hp3d_smpl_model* md, hp3d_smpl** out) {
   rc = rc ? rc : upload(&h->reg_col, rcol.data(), rcol.size());
   rc = rc ? rc : upload(&h->reg_val, rval.data(), rval.size());
   rc = rc ? rc : upload(&h->pick_ids, picks.data(), picks.size());
-  rc = rc ? rc : blend_tc_create(md->posedirs, &h->blend_tc);
+  rc = rc ? rc : upload(&h->tile_nq, tnq.data(), tnq.size());
+  rc = rc ? rc : upload(&h->tile_joff, tjoff.data(), tjoff.size());
+  rc = rc ? rc : upload(&h->tile_w, tw.data(), tw.size());
+  rc = rc ? rc : blend_tc_create(md->posedirs, md->shapedirs, md->v_template, &h->blend_tc);
   if (rc) { hp3d_smpl_destroy(h); return rc; }
   *out = h;
   return 0;
@@ -423,6 +615,7 @@ extern "C" void hp3d_smpl_destroy(hp3d_smpl* h) {
   cudaFree(h->v_template); cudaFree(h->shapedirs_t); cudaFree(h->posedirs); cudaFree(h->J_template);
   cudaFree(h->J_shapedirs); cudaFree(h->skin_idx); cudaFree(h->skin_w); cudaFree(h->reg_rowptr);
   cudaFree(h->reg_col); cudaFree(h->reg_val); cudaFree(h->pick_ids);
+  cudaFree(h->tile_nq); cudaFree(h->tile_joff); cudaFree(h->tile_w);
   blend_tc_destroy(h->blend_tc);
   delete h;
 }
@@ -456,12 +649,13 @@ static int blend_mode() {
   return g_blend_mode;
 }
 
-extern "C" int hp3d_smpl_pose_blend(const hp3d_smpl* h, const float* v_shaped, int Mb, const float* body_pose, int M,
-                                    float* v_posed, void* workspace, size_t workspace_bytes, void* stream) {
-  HP3D_ARG(h && v_shaped && body_pose && v_posed && M > 0 && Mb > 0 && M % Mb == 0, "bad argument");
+extern "C" int hp3d_smpl_pose_blend(const hp3d_smpl* h, const float* betas, const float* v_shaped, int Mb,
+                                    const float* body_pose, int M, float* v_posed, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  HP3D_ARG(h && betas && v_shaped && body_pose && v_posed && M > 0 && Mb > 0 && M % Mb == 0, "bad argument");
   if (blend_mode() == 1 && h->blend_tc) {
     HP3D_ARG(workspace && workspace_bytes >= blend_tc_workspace_bytes(M), "workspace too small (hp3d_smpl_pose_blend_workspace_bytes)");
-    return blend_tc_forward(h->blend_tc, v_shaped, Mb, body_pose, M, v_posed, workspace, (cudaStream_t)stream);
+    return blend_tc_forward(h->blend_tc, betas, Mb, body_pose, M, v_posed, workspace, (cudaStream_t)stream);
   }
   dim3 grid(cdiv(NV3, PB_BN), cdiv(M, PB_BM));
   pose_blend_fp32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(body_pose, h->posedirs, v_shaped, M, M / Mb, v_posed);
@@ -473,6 +667,20 @@ extern "C" int hp3d_smpl_lbs(const hp3d_smpl* h, const float* v_posed, const flo
                              float* joints, void* stream) {
   HP3D_ARG(h && v_posed && J && global_orient && body_pose && vertices, "null argument");
   HP3D_ARG(M > 0 && Mb > 0 && Mg > 0 && M % Mb == 0 && M % Mg == 0, "M must be a multiple of Mb and Mg");
+  static int force_generic = -1;
+  if (force_generic < 0) { const char* e = getenv("HP3D_LBS"); force_generic = (e && !strcmp(e, "generic")) ? 1 : 0; }
+  if (h->tile_nq_max > 0 && !force_generic) {
+    const int grid = cdiv(M, LBS_G);
+    if (h->tile_nq_max <= 8)
+      lbs_tile_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M, h->tile_nq,
+                                                                h->tile_joff, h->tile_w, h->reg_rowptr, h->reg_col,
+                                                                h->reg_val, h->pick_ids, h->tree, vertices, joints);
+    else
+      lbs_tile_kernel<NQCAP><<<grid, 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M, h->tile_nq,
+                                                                    h->tile_joff, h->tile_w, h->reg_rowptr, h->reg_col,
+                                                                    h->reg_val, h->pick_ids, h->tree, vertices, joints);
+    return launch_status("lbs_tile_kernel");
+  }
   const int grid = std::min(M, 148 * 8);
   lbs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M, h->skin_idx,
                                                       h->skin_w, h->skin_k, h->reg_rowptr, h->reg_col, h->reg_val,
@@ -492,7 +700,7 @@ extern "C" int hp3d_smpl_forward(const hp3d_smpl* h, const float* betas, int Mb,
   float* v_posed = (float*)ws; ws += ws_vposed(M);
   int rc = hp3d_smpl_shape_blend(h, betas, Mb, v_shaped, J, stream);
   if (rc) return rc;
-  rc = hp3d_smpl_pose_blend(h, v_shaped, Mb, body_pose, M, v_posed, ws, blend_tc_workspace_bytes(M), stream);
+  rc = hp3d_smpl_pose_blend(h, betas, v_shaped, Mb, body_pose, M, v_posed, ws, blend_tc_workspace_bytes(M), stream);
   if (rc) return rc;
   return hp3d_smpl_lbs(h, v_posed, J, Mb, global_orient, Mg, body_pose, M, vertices, joints, stream);
 }

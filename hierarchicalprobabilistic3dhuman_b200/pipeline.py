@@ -1,0 +1,125 @@
+"""Batched hot-path driver: the reference's per-image sequence
+(predict/predict_poseMF_shapeGaussian_net.py:102-165) for B images x N samples in one pass,
+
+    proxy rep -> encoder -> MF head -> rot6d -> SMPL(mode) -> MF sampler -> SMPL(B*N) -> per-vertex uncertainty
+
+with the two things a Python caller cannot get from the drop-in modules alone:
+  * outputs written straight into caller-provided (e.g. all-gather) buffers, no pack/copy;
+  * `run_host`: inputs in pinned HOST memory are streamed to the GPU in chunks on a copy stream while the
+    encoder already works on the chunks that have landed, results are read back on a third stream, and
+    consecutive calls overlap (double-buffered staging) -- PCIe, not the kernels, bounds this path.
+"""
+import torch
+
+from . import _lib
+from .rigid import rot6d_to_rotmat
+from .sampling import pose_matrix_fisher_sampling_torch
+
+
+class HotPathPipeline:
+    def __init__(self, net, smpl, batch, num_samples, device, rotmats_out=None, betas_out=None, vertices_out=None,
+                 uncertainty_out=None, chunks=4):
+        self.net, self.smpl, self.B, self.N, self.dev = net, smpl, batch, num_samples, torch.device(device)
+        B, N, dev = batch, num_samples, self.dev
+        mk = lambda t, *s: t if t is not None else torch.empty(*s, device=dev, dtype=torch.float32)
+        self.rotmats = mk(rotmats_out, B, N, 23, 3, 3)
+        self.betas = mk(betas_out, B, 10)
+        self.vertices = mk(vertices_out, B, N, 6890, 3)
+        self.uncertainty = mk(uncertainty_out, B, 6890)
+        for t in (self.rotmats, self.betas, self.vertices, self.uncertainty):
+            assert t.is_contiguous() and t.device == dev
+        self.joints = torch.empty(B * N, 90, 3, device=dev)
+        self.L = _lib.lib()
+        self.h_smpl = smpl._handle(dev)
+        self.ws = torch.empty(self.L.hp3d_smpl_workspace_bytes(self.h_smpl, B * N, B), dtype=torch.uint8, device=dev)
+        # host-streaming state
+        self.chunks = chunks if B % chunks == 0 else 1
+        self._stage = None
+        self._slot = 0
+        # kernels launched by one pass (ResNet-18 fast mode 23, head 6, rot6d 1, SMPL 4+4, sampler 1, stats 1, betas copy 1)
+        self.launches_per_pass = 23 + 6 + 1 + 4 + 1 + 4 + 1 + 1
+
+    # ------------------------------------------------------------------ device-resident pass
+    def _after_encoder(self, feats):
+        L, B, N = self.L, self.B, self.N
+        F, U, S, V, mode, shape_params, glob, cam = self.net.head(feats)
+        loc = shape_params[:, :10].contiguous()
+        glob_R = rot6d_to_rotmat(glob)
+        out_mode = self.smpl(body_pose=mode, global_orient=glob_R.unsqueeze(1), betas=loc, pose2rot=False)
+        R = pose_matrix_fisher_sampling_torch(U, S, V, N, out=self.rotmats)
+        self.betas.copy_(loc)
+        _lib.check(L.hp3d_smpl_forward(self.h_smpl, loc.data_ptr(), B, glob_R.data_ptr(), B, R.data_ptr(), B * N,
+                                       self.vertices.data_ptr(), self.joints.data_ptr(), self.ws.data_ptr(),
+                                       self.ws.numel(), _lib.stream_ptr()), "hp3d_smpl_forward")
+        _lib.check(L.hp3d_vertex_uncertainty(self.vertices.data_ptr(), B, N, None, self.uncertainty.data_ptr(),
+                                             _lib.stream_ptr()), "hp3d_vertex_uncertainty")
+        return dict(mode_vertices=out_mode.vertices, mode_joints=out_mode.joints, joints=self.joints, rotmats=R,
+                    uncertainty=self.uncertainty, vertices=self.vertices, betas=self.betas, pose_S=S, cam=cam)
+
+    def run_device(self, x_dev):
+        """x_dev (B,18,256,256) fp32 on the GPU -> dict of device tensors (sample vertices live in `vertices`)."""
+        with torch.cuda.device(self.dev):
+            return self._after_encoder(self.net.encode(x_dev))
+
+    # ------------------------------------------------------------------ host-streaming pass
+    def _staging(self, x_host):
+        if self._stage is None:
+            B, dev = self.B, self.dev
+            mk_host = lambda *s: torch.empty(*s, dtype=torch.float32).pin_memory()
+            self._stage = dict(
+                x=[torch.empty_like(x_host, device=dev) for _ in range(2)],
+                x_free=[None, None],                                   # event: encoder finished reading slot
+                out=[dict(mode_vertices=mk_host(B, 6890, 3), joints=mk_host(B * self.N, 90, 3),
+                          rotmats=mk_host(B, self.N, 23, 3, 3), uncertainty=mk_host(B, 6890)) for _ in range(2)],
+                out_done=[None, None],                                  # event: D2H of slot finished
+                h2d=torch.cuda.Stream(device=dev), d2h=torch.cuda.Stream(device=dev))
+        return self._stage
+
+    def run_host(self, x_host):
+        """x_host: pinned (B,18,256,256) fp32 HOST tensor. Returns (dict of pinned host result tensors, event);
+        the results are valid once `event.synchronize()` returns. Calls may be issued back to back: copies of
+        call i+1 overlap the kernels of call i."""
+        assert x_host.is_pinned() and x_host.shape[0] == self.B
+        st = self._staging(x_host)
+        slot = self._slot
+        self._slot ^= 1
+        B, C = self.B, self.chunks
+        cb = B // C
+        with torch.cuda.device(self.dev):
+            main = torch.cuda.current_stream()
+            xbuf = st["x"][slot]
+            evs = []
+            with torch.cuda.stream(st["h2d"]):
+                if st["x_free"][slot] is not None:
+                    st["h2d"].wait_event(st["x_free"][slot])           # encoder of two calls ago is done with the slot
+                for c in range(C):
+                    xbuf[c * cb:(c + 1) * cb].copy_(x_host[c * cb:(c + 1) * cb], non_blocking=True)
+                    e = torch.cuda.Event()
+                    e.record(st["h2d"])
+                    evs.append(e)
+            feats = []
+            for c in range(C):
+                main.wait_event(evs[c])
+                feats.append(self.net.encode(xbuf[c * cb:(c + 1) * cb]))
+            free = torch.cuda.Event()
+            free.record(main)
+            st["x_free"][slot] = free
+            if st["out_done"][slot ^ 1] is not None:
+                main.wait_event(st["out_done"][slot ^ 1])               # previous call's results have left the device buffers
+            res = self._after_encoder(torch.cat(feats) if C > 1 else feats[0])
+            done = torch.cuda.Event()
+            done.record(main)
+            out = st["out"][slot]
+            with torch.cuda.stream(st["d2h"]):
+                st["d2h"].wait_event(done)
+                for k in out:
+                    res[k].record_stream(st["d2h"])
+                    out[k].copy_(res[k], non_blocking=True)
+                fin = torch.cuda.Event()
+                fin.record(st["d2h"])
+            st["out_done"][slot] = fin
+        return out, fin
+
+    def d2h_bytes(self):
+        B, N = self.B, self.N
+        return 4 * (B * 6890 * 3 + B * N * 90 * 3 + B * N * 23 * 9 + B * 6890)

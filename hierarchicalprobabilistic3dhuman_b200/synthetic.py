@@ -69,8 +69,20 @@ def synthetic_smpl_model(seed=2, max_skin_nnz=4):
         if SMPL_PARENTS[j] >= 0:
             cand.append(int(SMPL_PARENTS[j]))
         cand += children[j]
-        while len(cand) < max_skin_nnz:
-            r = int(rs.randint(NUM_JOINTS))
+        # fill up with the next-nearest joints in the tree (grandparent, siblings, grandchildren), like the
+        # smooth, spatially coherent weights of the real model -- never with an unrelated random joint
+        ring = []
+        if SMPL_PARENTS[j] >= 0:
+            pj = int(SMPL_PARENTS[j])
+            if SMPL_PARENTS[pj] >= 0:
+                ring.append(int(SMPL_PARENTS[pj]))
+            ring += [c for c in children[pj] if c != j]
+        for c in children[j]:
+            ring += children[c]
+        ring += [(j + d) % NUM_JOINTS for d in (1, 2, 3)]
+        for r in ring:
+            if len(cand) >= max_skin_nnz:
+                break
             if r not in cand:
                 cand.append(r)
         cand = cand[:max_skin_nnz]

@@ -61,8 +61,8 @@ int hp3d_smpl_forward(const hp3d_smpl* h, const float* betas, int Mb, const floa
 int hp3d_smpl_shape_blend(const hp3d_smpl* h, const float* betas, int Mb, float* v_shaped /*[Mb*20672]*/,
                           float* J /*[Mb*24*3]*/, void* stream);
 size_t hp3d_smpl_pose_blend_workspace_bytes(int M);   /* fp16 hi/lo pose features for the tensor-core blend */
-int hp3d_smpl_pose_blend(const hp3d_smpl* h, const float* v_shaped, int Mb, const float* body_pose, int M,
-                         float* v_posed /*[M*20670]*/, void* workspace, size_t workspace_bytes, void* stream);
+int hp3d_smpl_pose_blend(const hp3d_smpl* h, const float* betas, const float* v_shaped, int Mb, const float* body_pose,
+                         int M, float* v_posed /*[M*20670]*/, void* workspace, size_t workspace_bytes, void* stream);
 int hp3d_smpl_lbs(const hp3d_smpl* h, const float* v_posed, const float* J, int Mb, const float* global_orient,
                   int Mg, const float* body_pose, int M, float* vertices, float* joints, void* stream);
 /* smplx batch_rodrigues: axis-angle [n*3] -> rotmats [n*9] (pose2rot=True callers:

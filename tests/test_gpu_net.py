@@ -104,3 +104,31 @@ def test_cpu_input_is_rejected(built_lib):
     m = hp.PoseMFShapeGaussianNet(syn.SMPL_PARENTS.tolist(), reference_config(), encoder_mode="parity")
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 18, 256, 256))
+
+
+def test_hot_path_pipeline_device_and_host_paths(built_lib):
+    """HotPathPipeline: device-resident pass, streamed-from-host pass and the drop-in modules agree."""
+    import hierarchicalprobabilistic3dhuman_b200 as hp
+    model = syn.synthetic_smpl_model()
+    smpl = hp.SMPL(model=model).cuda()
+    m = make_model("fast")
+    B, N = 8, 8
+    x = torch.from_numpy(syn.synthetic_proxy_rep(B, seed=5))
+    pipe = hp.HotPathPipeline(m, smpl, B, N, torch.device("cuda", 0))
+    res = pipe.run_device(x.cuda())
+    F, U, S, V, mode, dist, glob, cam = m(x.cuda())
+    ref_mode = smpl(body_pose=mode, global_orient=hp.rot6d_to_rotmat(glob).unsqueeze(1), betas=dist.loc, pose2rot=False)
+    assert torch.equal(res["mode_vertices"], ref_mode.vertices)
+    assert res["vertices"].shape == (B, N, 6890, 3) and torch.isfinite(res["vertices"]).all()
+    mean, d = hp.vertex_uncertainty(res["vertices"])
+    assert torch.equal(d, res["uncertainty"])
+    xh = x.pin_memory()
+    outs = []
+    for _ in range(3):                                   # back-to-back calls exercise the double buffering
+        out, ev = pipe.run_host(xh)
+        ev.synchronize()
+        outs.append({k: v.clone() for k, v in out.items()})
+    for o in outs:
+        assert torch.equal(o["mode_vertices"], ref_mode.vertices.cpu())
+        assert torch.isfinite(o["joints"]).all() and (torch.linalg.det(o["rotmats"]) - 1).abs().max() < 1e-5
+    assert not torch.equal(outs[0]["rotmats"], outs[1]["rotmats"])      # fresh Philox stream per call

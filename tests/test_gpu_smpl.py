@@ -50,7 +50,7 @@ def test_stage_outputs_match_oracle(setup):
     b, p = betas.cuda(), pose.cuda().contiguous()
     _lib.check(L.hp3d_smpl_shape_blend(h, b.data_ptr(), M, vs.data_ptr(), J.data_ptr(), None))
     wsb = torch.empty(L.hp3d_smpl_pose_blend_workspace_bytes(M), dtype=torch.uint8, device="cuda")
-    _lib.check(L.hp3d_smpl_pose_blend(h, vs.data_ptr(), M, p.data_ptr(), M, vp.data_ptr(), wsb.data_ptr(), wsb.numel(), None))
+    _lib.check(L.hp3d_smpl_pose_blend(h, b.data_ptr(), vs.data_ptr(), M, p.data_ptr(), M, vp.data_ptr(), wsb.data_ptr(), wsb.numel(), None))
     torch.cuda.synchronize()
     assert rel_err(vs[:, :20670].reshape(M, 6890, 3), ref["v_shaped"]) < 1e-6
     assert rel_err(J, ref["J"]) < 1e-5
@@ -136,3 +136,59 @@ def test_errors_are_loud(setup):
         smpl(betas=torch.zeros(1, 10), body_pose=torch.eye(3).expand(1, 23, 3, 3), global_orient=torch.eye(3).expand(1, 1, 3, 3), pose2rot=False)
     with pytest.raises(ValueError):
         smpl(betas=torch.zeros(2, 10).cuda(), body_pose=torch.eye(3).expand(3, 23, 3, 3).cuda(), global_orient=torch.eye(3).expand(3, 1, 3, 3).cuda(), pose2rot=False)
+
+
+def _tile_nq_max(model):
+    W = model["lbs_weights"]
+    return max(int((W[t * 64:(t + 1) * 64] != 0).any(0).sum()) for t in range(108))
+
+
+@pytest.mark.parametrize("variant", ["tile8", "tile12", "generic"])
+def test_all_skinning_kernel_variants(built_lib, variant):
+    """The tile-local LBS kernel (<=8 / <=12 joints per 64-vertex tile) and the generic per-vertex gather
+    kernel (models without spatial coherence) must agree with the oracle."""
+    import hierarchicalprobabilistic3dhuman_b200 as hp
+    model = syn.synthetic_smpl_model()
+    rs = np.random.RandomState(3)
+    W = model["lbs_weights"].copy()
+    if variant == "tile12":          # shuffle rows inside windows of 700 vertices: tiles see more joints
+        for s in range(0, 6890, 700):
+            idx = np.arange(s, min(s + 700, 6890)); W[idx] = W[rs.permutation(idx)]
+    elif variant == "generic":       # no coherence at all
+        W = W[rs.permutation(6890)]
+    model["lbs_weights"] = W
+    nq = _tile_nq_max(model)
+    assert {"tile8": nq <= 8, "tile12": 8 < nq <= 12, "generic": nq > 12}[variant], nq
+    smpl = hp.SMPL(model=model).cuda()
+    oracle = SMPLOracle(model, torch.float64)
+    for M in (3, 17):
+        betas, pose, glob = _rand(np.random.RandomState(40 + M), M)
+        out = smpl(betas=betas.cuda(), body_pose=pose.cuda(), global_orient=glob.cuda(), pose2rot=False)
+        ref = oracle.forward(betas, pose, glob)
+        assert rel_err(out.vertices, ref["vertices"]) < TOL and rel_err(out.joints, ref["joints"]) < TOL
+
+
+def test_full_size_smpl_properties(built_lib):
+    """BASELINE configs[1] size (64 x 100 meshes): linearity in the global rotation and finiteness."""
+    import hierarchicalprobabilistic3dhuman_b200 as hp
+    model = syn.synthetic_smpl_model()
+    smpl = hp.SMPL(model=model).cuda()
+    rs = np.random.RandomState(12)
+    B, N = 64, 100
+    pose = torch.as_tensor(syn.random_rotmats(rs, (B * N, 23)), dtype=torch.float32).cuda()
+    glob = torch.as_tensor(syn.random_rotmats(rs, (B, 1)), dtype=torch.float32).cuda()
+    betas = torch.as_tensor(rs.normal(0, 1.25, size=(B, 10)), dtype=torch.float32).cuda()
+    out = smpl(betas=betas, body_pose=pose, global_orient=glob, pose2rot=False)
+    eye = torch.eye(3, device="cuda").expand(B, 1, 3, 3).contiguous()
+    base = smpl(betas=betas, body_pose=pose, global_orient=eye, pose2rot=False)
+    assert torch.isfinite(out.vertices).all()
+    # global orientation acts rigidly about the (shape-dependent) root joint
+    root = base.joints[:, 0:1]                                         # (M,1,3) posed root == J_0
+    Rg = glob[:, 0].repeat_interleave(N, 0)
+    expect = torch.einsum("mij,mvj->mvi", Rg, base.vertices - root) + root
+    assert rel_err(out.vertices, expect) < 1e-5
+    # spot-check 3 meshes against the oracle
+    oracle = SMPLOracle(model, torch.float64)
+    idx = [0, 3217, B * N - 1]
+    ref = oracle.forward(betas.cpu()[[i // N for i in idx]], pose.cpu()[idx], glob.cpu()[[i // N for i in idx]])
+    assert rel_err(out.vertices[idx], ref["vertices"]) < TOL and rel_err(out.joints[idx], ref["joints"]) < TOL
