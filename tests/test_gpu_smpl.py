@@ -151,9 +151,9 @@ def test_all_skinning_kernel_variants(built_lib, variant):
     model = syn.synthetic_smpl_model()
     rs = np.random.RandomState(3)
     W = model["lbs_weights"].copy()
-    if variant == "tile12":          # shuffle rows inside windows of 700 vertices: tiles see more joints
-        for s in range(0, 6890, 700):
-            idx = np.arange(s, min(s + 700, 6890)); W[idx] = W[rs.permutation(idx)]
+    if variant == "tile12":          # shuffle rows inside windows of 420 vertices: tiles see more joints
+        for s in range(0, 6890, 420):
+            idx = np.arange(s, min(s + 420, 6890)); W[idx] = W[rs.permutation(idx)]
     elif variant == "generic":       # no coherence at all
         W = W[rs.permutation(6890)]
     model["lbs_weights"] = W
