@@ -81,7 +81,8 @@ blend_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
                 const __grid_constant__ BlendArgs args) {
   using L = BlendSmem<PASSES>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // pointer arithmetic on the extern array (not an integer round trip) keeps the shared address space visible to ptxas
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
@@ -205,10 +206,19 @@ blend_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
           const int n = nt * BN + ch * 32 + lane;
           if (n < NV3) {
             float* dst = args.v_posed + (size_t)m_base * NV3 + n;
-            const int rows = min(32, args.M - m_base);
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr)
-              if (rr < rows) dst[(size_t)rr * NV3] = stg[rr * 33 + lane] * args.inv_scale;
+            const int rows = args.M - m_base;
+            if (rows >= 32) {                         // full tile: batch the shared-memory reads, then the stores
+#pragma unroll
+              for (int r0 = 0; r0 < 32; r0 += 8) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = stg[(r0 + e) * 33 + lane] * args.inv_scale;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dst[(size_t)(r0 + e) * NV3] = v[e];
+              }
+            } else {
+              for (int rr = 0; rr < rows; ++rr) dst[(size_t)rr * NV3] = stg[rr * 33 + lane] * args.inv_scale;
+            }
           }
           __syncwarp();
         }

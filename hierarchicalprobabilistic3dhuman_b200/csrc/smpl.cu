@@ -277,9 +277,10 @@ constexpr int TV = 64;                      // vertices per tile
 constexpr int NT = (NV + TV - 1) / TV;      // 108
 constexpr int NQCAP = 12;
 constexpr int LBS_G = 8;                    // meshes per CTA (== warps per CTA)
+constexpr int LBS_D = 6;                    // cp.async ring depth per warp (items of 768 B)
 
 template <int NQMAX>
-__global__ void __launch_bounds__(256, 2) lbs_tile_kernel(const float* __restrict__ v_posed, const float* __restrict__ J,
+__global__ void __launch_bounds__(256, 3) lbs_tile_kernel(const float* __restrict__ v_posed, const float* __restrict__ J,
                                                           int Mb, const float* __restrict__ global_orient, int Mg,
                                                           const float* __restrict__ body_pose, int M,
                                                           const int* __restrict__ tile_nq, const int* __restrict__ tile_joff,
@@ -289,7 +290,8 @@ __global__ void __launch_bounds__(256, 2) lbs_tile_kernel(const float* __restric
                                                           SmplTree tree, float* __restrict__ vertices,
                                                           float* __restrict__ joints) {
   __shared__ float4 sA[LBS_G][NJ * 3];
-  __shared__ float sG[LBS_G][NJ][12];
+  __shared__ __align__(16) float ring_all[8 * LBS_D * 192];   // per-warp cp.async rings, 768 B slots (phase 2)
+  float (*sG)[NJ][12] = reinterpret_cast<float (*)[NJ][12]>(ring_all);   // FK scratch (phase 1) aliases the rings
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int repb = M / Mb, repg = M / Mg;
   const int m0 = blockIdx.x * LBS_G;
@@ -342,38 +344,68 @@ __global__ void __launch_bounds__(256, 2) lbs_tile_kernel(const float* __restric
     }
   }
   __syncthreads();
-  // ---- phase 2: skinning, warp sweeps tiles, meshes innermost (weights stay in registers)
-  for (int tile = warp; tile < NT; tile += 8) {
-    const int nq = tile_nq[tile];
-    const int v0 = tile * TV + 2 * lane;
-    const bool valid = v0 < NV;                       // NV is even: a lane's two vertices are both in or out
-    float w0[NQMAX], w1[NQMAX];
-    int joff[NQMAX];
+  // ---- phase 2: skinning. Each warp streams its (tile, mesh) items through a private ring of LBS_D
+  // shared-memory slots filled by cp.async (8-byte, fully coalesced: lane l moves bytes [8l, 8l+8) of each
+  // 256-byte third of the 768-byte item), so LBS_D-1 items of HBM latency are in flight per warp without
+  // holding registers; lanes then read "their" two vertices (24 B) back with conflict-free LDS.64, and
+  // results leave through the same slot with coalesced 8-byte stores.
+  {
+    float* ring = ring_all + warp * (LBS_D * 192);
+    const int my_tiles = (NT - warp + 7) / 8;             // tiles warp, warp+8, ...
+    const int n_items = my_tiles * Gv;
+    auto issue = [&](int it) {
+      if (it < n_items) {
+        const int tile = warp + 8 * (it / Gv), g = it - (it / Gv) * Gv;
+        const int nfl = min(TV, NV - tile * TV) * 3;       // floats in this tile (192, last tile 126)
+        const float* src = v_posed + (size_t)(m0 + g) * NV3 + (size_t)tile * (TV * 3);
+        float* dst = ring + (it % LBS_D) * 192;
 #pragma unroll
-    for (int q = 0; q < NQMAX; ++q) {
-      w0[q] = 0.f; w1[q] = 0.f; joff[q] = 0;
-      if (q < nq) {
-        const float2 w = *reinterpret_cast<const float2*>(tile_w + ((size_t)tile * NQCAP + q) * TV + 2 * lane);
-        w0[q] = w.x; w1[q] = w.y;
-        joff[q] = tile_joff[tile * NQCAP + q];
+        for (int i = 0; i < 3; ++i) {
+          const int f = 2 * lane + 64 * i;
+          if (f < nfl)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + f)), "l"(src + f) : "memory");
+        }
       }
-    }
-    const size_t voff = (size_t)3 * v0;
-#pragma unroll 2
-    for (int g = 0; g < Gv; ++g) {
-      const float* src = v_posed + (size_t)(m0 + g) * NV3 + voff;
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int it = 0; it < LBS_D - 1; ++it) issue(it);
+    float w0[NQMAX], w1[NQMAX];
+    uint32_t jpack[(NQMAX + 3) / 4];
+    int nq = 0;
+    for (int it = 0; it < n_items; ++it) {
+      const int tile = warp + 8 * (it / Gv), g = it - (it / Gv) * Gv;
+      if (g == 0) {                                        // new tile: (re)load its joint list and my two weight columns
+        nq = tile_nq[tile];
+#pragma unroll
+        for (int q = 0; q < (NQMAX + 3) / 4; ++q) jpack[q] = 0;
+#pragma unroll
+        for (int q = 0; q < NQMAX; ++q) {
+          w0[q] = 0.f; w1[q] = 0.f;
+          if (q < nq) {
+            const float2 w = *reinterpret_cast<const float2*>(tile_w + ((size_t)tile * NQCAP + q) * TV + 2 * lane);
+            w0[q] = w.x; w1[q] = w.y;
+            jpack[q >> 2] |= (uint32_t)tile_joff[tile * NQCAP + q] << (8 * (q & 3));
+          }
+        }
+      }
+      issue(it + LBS_D - 1);
+      asm volatile("cp.async.wait_group %0;" ::"n"(LBS_D - 1) : "memory");
+      __syncwarp();
+      float* slot = ring + (it % LBS_D) * 192;
+      const bool valid = tile * TV + 2 * lane < NV;        // NV is even: a lane's two vertices are both in or out
       float2 p0 = make_float2(0.f, 0.f), p1 = p0, p2 = p0;
       if (valid) {
-        p0 = *reinterpret_cast<const float2*>(src);
-        p1 = *reinterpret_cast<const float2*>(src + 2);
-        p2 = *reinterpret_cast<const float2*>(src + 4);
+        p0 = *reinterpret_cast<const float2*>(slot + 6 * lane);
+        p1 = *reinterpret_cast<const float2*>(slot + 6 * lane + 2);
+        p2 = *reinterpret_cast<const float2*>(slot + 6 * lane + 4);
       }
       float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, b0 = a0, b1 = a0, b2 = a0;
       const float4* Ag = sA[g];
 #pragma unroll
       for (int q = 0; q < NQMAX; ++q) {
         if (q < nq) {
-          const float4 r0 = Ag[joff[q]], r1 = Ag[joff[q] + 1], r2 = Ag[joff[q] + 2];
+          const int jo = (jpack[q >> 2] >> (8 * (q & 3))) & 0xFF;
+          const float4 r0 = Ag[jo], r1 = Ag[jo + 1], r2 = Ag[jo + 2];
           const float u = w0[q], v = w1[q];
           a0.x = fmaf(u, r0.x, a0.x); a0.y = fmaf(u, r0.y, a0.y); a0.z = fmaf(u, r0.z, a0.z); a0.w = fmaf(u, r0.w, a0.w);
           a1.x = fmaf(u, r1.x, a1.x); a1.y = fmaf(u, r1.y, a1.y); a1.z = fmaf(u, r1.z, a1.z); a1.w = fmaf(u, r1.w, a1.w);
@@ -383,6 +415,7 @@ __global__ void __launch_bounds__(256, 2) lbs_tile_kernel(const float* __restric
           b2.x = fmaf(v, r2.x, b2.x); b2.y = fmaf(v, r2.y, b2.y); b2.z = fmaf(v, r2.z, b2.z); b2.w = fmaf(v, r2.w, b2.w);
         }
       }
+      __syncwarp();                                        // everyone has read the slot: reuse it for the results
       if (valid) {
         const float x0 = p0.x, y0 = p0.y, z0 = p1.x, x1 = p1.y, y1 = p2.x, z1 = p2.y;
         float2 o0, o1, o2;
@@ -392,12 +425,23 @@ __global__ void __launch_bounds__(256, 2) lbs_tile_kernel(const float* __restric
         o1.y = fmaf(b0.z, z1, fmaf(b0.y, y1, b0.x * x1)) + b0.w;
         o2.x = fmaf(b1.z, z1, fmaf(b1.y, y1, b1.x * x1)) + b1.w;
         o2.y = fmaf(b2.z, z1, fmaf(b2.y, y1, b2.x * x1)) + b2.w;
-        float* dst = vertices + (size_t)(m0 + g) * NV3 + voff;
-        *reinterpret_cast<float2*>(dst) = o0;
-        *reinterpret_cast<float2*>(dst + 2) = o1;
-        *reinterpret_cast<float2*>(dst + 4) = o2;
+        *reinterpret_cast<float2*>(slot + 6 * lane) = o0;
+        *reinterpret_cast<float2*>(slot + 6 * lane + 2) = o1;
+        *reinterpret_cast<float2*>(slot + 6 * lane + 4) = o2;
       }
+      __syncwarp();
+      {
+        const int nfl = min(TV, NV - tile * TV) * 3;
+        float* dst = vertices + (size_t)(m0 + g) * NV3 + (size_t)tile * (TV * 3);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const int f = 2 * lane + 64 * i;
+          if (f < nfl) *reinterpret_cast<float2*>(dst + f) = *reinterpret_cast<const float2*>(slot + f);
+        }
+      }
+      __syncwarp();                                        // slot may be refilled by the next issue()
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   if (!joints) return;
   __syncthreads();
