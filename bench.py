@@ -211,25 +211,18 @@ def main_hp3d(args):
     torch.manual_seed(1234 + rank)
 
     # gather buffers: every rank's kernels write straight into its slice (no pack/copy)
+    from hierarchicalprobabilistic3dhuman_b200.distributed import GatherBuffers
     full = args.gather == "full"
-    g_rot = torch.empty(world * B, N, 23, 3, 3, device=dev)
-    g_betas = torch.empty(world * B, 10, device=dev)
-    g_verts = torch.empty(world * B if full else B, N, 6890, 3, device=dev)
-    g_unc = torch.empty(world * B, 6890, device=dev)
-    sl = slice(rank * B, (rank + 1) * B)
-    vsl = sl if full else slice(0, B)
-    pipe = hp.HotPathPipeline(net, smpl, B, N, dev, rotmats_out=g_rot[sl], betas_out=g_betas[sl],
-                              vertices_out=g_verts[vsl], uncertainty_out=g_unc[sl])
+    specs = {"rotmats": (N, 23, 3, 3), "betas": (10,), "uncertainty": (6890,)}
+    if full:
+        specs["vertices"] = (N, 6890, 3)
+    gb = GatherBuffers(B, specs, dev, rank=rank, world=world)
+    verts_local = gb.local("vertices") if full else torch.empty(B, N, 6890, 3, device=dev)
+    pipe = hp.HotPathPipeline(net, smpl, B, N, dev, rotmats_out=gb.local("rotmats"), betas_out=gb.local("betas"),
+                              vertices_out=verts_local, uncertainty_out=gb.local("uncertainty"))
     L = _lib.lib()
     h_smpl, joints = pipe.h_smpl, pipe.joints
-
-    def gather():
-        if world > 1:
-            dist.all_gather_into_tensor(g_rot, g_rot[sl])
-            dist.all_gather_into_tensor(g_betas, g_betas[sl])
-            dist.all_gather_into_tensor(g_unc, g_unc[sl])
-            if full:
-                dist.all_gather_into_tensor(g_verts, g_verts[sl])
+    gather = gb.all_gather
 
     def step(x):
         pipe.run_device(x)
@@ -285,16 +278,16 @@ def main_hp3d(args):
     vp = torch.empty(M, 20670, device=dev).normal_()
     Jt = torch.randn(B, 24, 3, device=dev)
     gR = hp.rot6d_to_rotmat(torch.randn(B, 6, device=dev))
-    Rr = g_rot[sl].contiguous()
+    Rr = gb.local("rotmats").contiguous()
     for _ in range(3):
         _lib.check(L.hp3d_smpl_lbs(h_smpl, vp.data_ptr(), Jt.data_ptr(), B, gR.data_ptr(), B, Rr.data_ptr(), M,
-                                   g_verts[vsl].data_ptr(), joints.data_ptr(), _lib.stream_ptr()))
+                                   verts_local.data_ptr(), joints.data_ptr(), _lib.stream_ptr()))
     torch.cuda.synchronize()
     reps = 5
     e0.record()
     for _ in range(reps):
         _lib.check(L.hp3d_smpl_lbs(h_smpl, vp.data_ptr(), Jt.data_ptr(), B, gR.data_ptr(), B, Rr.data_ptr(), M,
-                                   g_verts[vsl].data_ptr(), joints.data_ptr(), _lib.stream_ptr()))
+                                   verts_local.data_ptr(), joints.data_ptr(), _lib.stream_ptr()))
     e1.record()
     torch.cuda.synchronize()
     lbs_ms = e0.elapsed_time(e1) / reps

@@ -277,10 +277,11 @@ constexpr int TV = 64;                      // vertices per tile
 constexpr int NT = (NV + TV - 1) / TV;      // 108
 constexpr int NQCAP = 12;
 constexpr int LBS_G = 8;                    // meshes per CTA (== warps per CTA)
-constexpr int LBS_D = 6;                    // cp.async ring depth per warp (items of 768 B)
+constexpr int LBS_D = 6;                    // bulk-copy ring depth per warp
+constexpr int SLOT_F = 196;                 // floats per ring slot (784 B = 768 + alignment window)
 
-template <int NQMAX>
-__global__ void __launch_bounds__(256, 3) lbs_tile_kernel(const float* __restrict__ v_posed, const float* __restrict__ J,
+template <int NQMAX, int MODE>   // MODE 2: register prefetch (distance 2), direct 8-byte loads; MODE 4: per-warp TMA bulk-copy ring
+__global__ void __launch_bounds__(256, MODE == 4 ? 3 : 2) lbs_tile_kernel(const float* __restrict__ v_posed, const float* __restrict__ J,
                                                           int Mb, const float* __restrict__ global_orient, int Mg,
                                                           const float* __restrict__ body_pose, int M,
                                                           const int* __restrict__ tile_nq, const int* __restrict__ tile_joff,
@@ -290,8 +291,13 @@ __global__ void __launch_bounds__(256, 3) lbs_tile_kernel(const float* __restric
                                                           SmplTree tree, float* __restrict__ vertices,
                                                           float* __restrict__ joints) {
   __shared__ float4 sA[LBS_G][NJ * 3];
-  __shared__ __align__(16) float ring_all[8 * LBS_D * 192];   // per-warp cp.async rings, 768 B slots (phase 2)
+  __shared__ __align__(16) float ring_all[8 * LBS_D * SLOT_F];   // per-warp bulk-copy rings, 784 B slots (phase 2)
+  __shared__ __align__(8) uint64_t ring_bars[8 * LBS_D];
   float (*sG)[NJ][12] = reinterpret_cast<float (*)[NJ][12]>(ring_all);   // FK scratch (phase 1) aliases the rings
+  if (MODE == 4 && threadIdx.x < 8 * LBS_D) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(ring_bars + threadIdx.x)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int repb = M / Mb, repg = M / Mg;
   const int m0 = blockIdx.x * LBS_G;
@@ -344,29 +350,112 @@ __global__ void __launch_bounds__(256, 3) lbs_tile_kernel(const float* __restric
     }
   }
   __syncthreads();
+  // ---- phase 2 (MODE 2): skinning, warp sweeps its tiles, meshes innermost; the two vertices of a lane are
+  // loaded/stored with 8-byte accesses straight from/to HBM, the loads of the next two meshes are issued
+  // before the current two are skinned (software prefetch, distance 2).
+  if constexpr (MODE == 2) {
+    for (int tile = warp; tile < NT; tile += 8) {
+      const int nq = tile_nq[tile];
+      const int v0 = tile * TV + 2 * lane;
+      const bool valid = v0 < NV;                       // NV is even: a lane's two vertices are both in or out
+      float w0[NQMAX], w1[NQMAX];
+      uint32_t jpack[(NQMAX + 3) / 4];
+#pragma unroll
+      for (int q = 0; q < (NQMAX + 3) / 4; ++q) jpack[q] = 0;
+#pragma unroll
+      for (int q = 0; q < NQMAX; ++q) {
+        w0[q] = 0.f; w1[q] = 0.f;
+        if (q < nq) {
+          const float2 w = *reinterpret_cast<const float2*>(tile_w + ((size_t)tile * NQCAP + q) * TV + 2 * lane);
+          w0[q] = w.x; w1[q] = w.y;
+          jpack[q >> 2] |= (uint32_t)tile_joff[tile * NQCAP + q] << (8 * (q & 3));
+        }
+      }
+      const size_t voff = (size_t)3 * v0;
+      const float* src0 = v_posed + (size_t)m0 * NV3 + voff;
+      float* dst0 = vertices + (size_t)m0 * NV3 + voff;
+      float2 pa[3], pb[3], na[3], nb[3];
+      auto ld = [&](int g, float2 (&p)[3]) {
+        p[0] = p[1] = p[2] = make_float2(0.f, 0.f);
+        if (valid && g < Gv) {
+          const float* s_ = src0 + (size_t)g * NV3;
+          p[0] = *reinterpret_cast<const float2*>(s_);
+          p[1] = *reinterpret_cast<const float2*>(s_ + 2);
+          p[2] = *reinterpret_cast<const float2*>(s_ + 4);
+        }
+      };
+      auto skin = [&](int g, const float2 (&p)[3]) {
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, b0 = a0, b1 = a0, b2 = a0;
+        const float4* Ag = sA[g];
+#pragma unroll
+        for (int q = 0; q < NQMAX; ++q) {
+          if (q < nq) {
+            const int jo = (jpack[q >> 2] >> (8 * (q & 3))) & 0xFF;
+            const float4 r0 = Ag[jo], r1 = Ag[jo + 1], r2 = Ag[jo + 2];
+            const float u = w0[q], v = w1[q];
+            a0.x = fmaf(u, r0.x, a0.x); a0.y = fmaf(u, r0.y, a0.y); a0.z = fmaf(u, r0.z, a0.z); a0.w = fmaf(u, r0.w, a0.w);
+            a1.x = fmaf(u, r1.x, a1.x); a1.y = fmaf(u, r1.y, a1.y); a1.z = fmaf(u, r1.z, a1.z); a1.w = fmaf(u, r1.w, a1.w);
+            a2.x = fmaf(u, r2.x, a2.x); a2.y = fmaf(u, r2.y, a2.y); a2.z = fmaf(u, r2.z, a2.z); a2.w = fmaf(u, r2.w, a2.w);
+            b0.x = fmaf(v, r0.x, b0.x); b0.y = fmaf(v, r0.y, b0.y); b0.z = fmaf(v, r0.z, b0.z); b0.w = fmaf(v, r0.w, b0.w);
+            b1.x = fmaf(v, r1.x, b1.x); b1.y = fmaf(v, r1.y, b1.y); b1.z = fmaf(v, r1.z, b1.z); b1.w = fmaf(v, r1.w, b1.w);
+            b2.x = fmaf(v, r2.x, b2.x); b2.y = fmaf(v, r2.y, b2.y); b2.z = fmaf(v, r2.z, b2.z); b2.w = fmaf(v, r2.w, b2.w);
+          }
+        }
+        if (valid) {
+          const float x0 = p[0].x, y0 = p[0].y, z0 = p[1].x, x1 = p[1].y, y1 = p[2].x, z1 = p[2].y;
+          float2 o0, o1, o2;
+          o0.x = fmaf(a0.z, z0, fmaf(a0.y, y0, a0.x * x0)) + a0.w;
+          o0.y = fmaf(a1.z, z0, fmaf(a1.y, y0, a1.x * x0)) + a1.w;
+          o1.x = fmaf(a2.z, z0, fmaf(a2.y, y0, a2.x * x0)) + a2.w;
+          o1.y = fmaf(b0.z, z1, fmaf(b0.y, y1, b0.x * x1)) + b0.w;
+          o2.x = fmaf(b1.z, z1, fmaf(b1.y, y1, b1.x * x1)) + b1.w;
+          o2.y = fmaf(b2.z, z1, fmaf(b2.y, y1, b2.x * x1)) + b2.w;
+          float* d_ = dst0 + (size_t)g * NV3;
+          *reinterpret_cast<float2*>(d_) = o0;
+          *reinterpret_cast<float2*>(d_ + 2) = o1;
+          *reinterpret_cast<float2*>(d_ + 4) = o2;
+        }
+      };
+      ld(0, pa); ld(1, pb);
+      for (int g = 0; g < Gv; g += 2) {
+        ld(g + 2, na); ld(g + 3, nb);
+        skin(g, pa);
+        if (g + 1 < Gv) skin(g + 1, pb);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) { pa[e] = na[e]; pb[e] = nb[e]; }
+      }
+    }
+  }
   // ---- phase 2: skinning. Each warp streams its (tile, mesh) items through a private ring of LBS_D
   // shared-memory slots filled by cp.async (8-byte, fully coalesced: lane l moves bytes [8l, 8l+8) of each
   // 256-byte third of the 768-byte item), so LBS_D-1 items of HBM latency are in flight per warp without
   // holding registers; lanes then read "their" two vertices (24 B) back with conflict-free LDS.64, and
   // results leave through the same slot with coalesced 8-byte stores.
-  {
-    float* ring = ring_all + warp * (LBS_D * 192);
+  // ---- phase 2 (MODE 4): the same skinning, but the vertex stream is staged by the TMA engine: every warp owns a
+  // ring of LBS_D shared-memory slots; lane 0 issues one cp.async.bulk (<= 784 B, 16-byte aligned window around
+  // the 768-byte (tile, mesh) item -- mesh rows are only 8-byte aligned, the window start is rounded down) per item
+  // and an mbarrier per slot signals arrival, so LBS_D-1 items of HBM latency are in flight per warp with no
+  // registers and no LSU instructions spent on the loads.
+  if constexpr (MODE == 4) {
+    float* ring = ring_all + warp * (LBS_D * SLOT_F);
+    uint64_t* bars = ring_bars + warp * LBS_D;
     const int my_tiles = (NT - warp + 7) / 8;             // tiles warp, warp+8, ...
     const int n_items = my_tiles * Gv;
     auto issue = [&](int it) {
-      if (it < n_items) {
+      if (it < n_items && lane == 0) {
         const int tile = warp + 8 * (it / Gv), g = it - (it / Gv) * Gv;
         const int nfl = min(TV, NV - tile * TV) * 3;       // floats in this tile (192, last tile 126)
         const float* src = v_posed + (size_t)(m0 + g) * NV3 + (size_t)tile * (TV * 3);
-        float* dst = ring + (it % LBS_D) * 192;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const int f = 2 * lane + 64 * i;
-          if (f < nfl)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + f)), "l"(src + f) : "memory");
-        }
+        const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
+        const uint32_t shift = (uint32_t)(sa & 15);        // 0 or 8 bytes
+        uint32_t bytes = (shift + (uint32_t)nfl * 4 + 15u) & ~15u;
+        if (bytes > shift + (uint32_t)nfl * 4 && tile == NT - 1 && m0 + g == M - 1) bytes -= 16;   // never read past the buffer
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (it % LBS_D) * SLOT_F);
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(bars + (it % LBS_D));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(sa - shift), "r"(bytes), "r"(bar) : "memory");
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
     };
     for (int it = 0; it < LBS_D - 1; ++it) issue(it);
     float w0[NQMAX], w1[NQMAX];
@@ -389,15 +478,34 @@ __global__ void __launch_bounds__(256, 3) lbs_tile_kernel(const float* __restric
         }
       }
       issue(it + LBS_D - 1);
-      asm volatile("cp.async.wait_group %0;" ::"n"(LBS_D - 1) : "memory");
-      __syncwarp();
-      float* slot = ring + (it % LBS_D) * 192;
+      {   // wait for this item's slot (parity flips every LBS_D items)
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(bars + (it % LBS_D));
+        const uint32_t parity = (uint32_t)((it / LBS_D) & 1);
+        uint32_t ok = 0;
+        long long t0 = 0;
+        while (true) {
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+          if (ok) break;
+          if (t0 == 0) t0 = clock64();
+          else if (clock64() - t0 > 4000000000ll) { printf("libhp3d: lbs bulk-copy wait timed out (block %d warp %d item %d)\n", (int)blockIdx.x, warp, it); __trap(); }
+        }
+      }
+      const float* src = v_posed + (size_t)(m0 + g) * NV3 + (size_t)tile * (TV * 3);
+      const int shift_f = (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 2);   // 0 or 2 floats
+      const float* slot = ring + (it % LBS_D) * SLOT_F + shift_f;
       const bool valid = tile * TV + 2 * lane < NV;        // NV is even: a lane's two vertices are both in or out
       float2 p0 = make_float2(0.f, 0.f), p1 = p0, p2 = p0;
       if (valid) {
         p0 = *reinterpret_cast<const float2*>(slot + 6 * lane);
         p1 = *reinterpret_cast<const float2*>(slot + 6 * lane + 2);
         p2 = *reinterpret_cast<const float2*>(slot + 6 * lane + 4);
+        if (tile == NT - 1 && m0 + g == M - 1 && (6 * lane + 6) * 4 + shift_f * 4 > ((shift_f * 4 + 126 * 4 + 15) & ~15) - 16) {
+          // the very last item of the buffer was clipped by 16 B: fetch the tail directly
+          p0 = *reinterpret_cast<const float2*>(src + 6 * lane);
+          p1 = *reinterpret_cast<const float2*>(src + 6 * lane + 2);
+          p2 = *reinterpret_cast<const float2*>(src + 6 * lane + 4);
+        }
       }
       float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, b0 = a0, b1 = a0, b2 = a0;
       const float4* Ag = sA[g];
@@ -415,7 +523,6 @@ __global__ void __launch_bounds__(256, 3) lbs_tile_kernel(const float* __restric
           b2.x = fmaf(v, r2.x, b2.x); b2.y = fmaf(v, r2.y, b2.y); b2.z = fmaf(v, r2.z, b2.z); b2.w = fmaf(v, r2.w, b2.w);
         }
       }
-      __syncwarp();                                        // everyone has read the slot: reuse it for the results
       if (valid) {
         const float x0 = p0.x, y0 = p0.y, z0 = p1.x, x1 = p1.y, y1 = p2.x, z1 = p2.y;
         float2 o0, o1, o2;
@@ -425,23 +532,13 @@ __global__ void __launch_bounds__(256, 3) lbs_tile_kernel(const float* __restric
         o1.y = fmaf(b0.z, z1, fmaf(b0.y, y1, b0.x * x1)) + b0.w;
         o2.x = fmaf(b1.z, z1, fmaf(b1.y, y1, b1.x * x1)) + b1.w;
         o2.y = fmaf(b2.z, z1, fmaf(b2.y, y1, b2.x * x1)) + b2.w;
-        *reinterpret_cast<float2*>(slot + 6 * lane) = o0;
-        *reinterpret_cast<float2*>(slot + 6 * lane + 2) = o1;
-        *reinterpret_cast<float2*>(slot + 6 * lane + 4) = o2;
+        float* dst = vertices + (size_t)(m0 + g) * NV3 + (size_t)tile * (TV * 3) + 6 * lane;
+        *reinterpret_cast<float2*>(dst) = o0;
+        *reinterpret_cast<float2*>(dst + 2) = o1;
+        *reinterpret_cast<float2*>(dst + 4) = o2;
       }
-      __syncwarp();
-      {
-        const int nfl = min(TV, NV - tile * TV) * 3;
-        float* dst = vertices + (size_t)(m0 + g) * NV3 + (size_t)tile * (TV * 3);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          const int f = 2 * lane + 64 * i;
-          if (f < nfl) *reinterpret_cast<float2*>(dst + f) = *reinterpret_cast<const float2*>(slot + f);
-        }
-      }
-      __syncwarp();                                        // slot may be refilled by the next issue()
+      __syncwarp();                                        // every lane has read the slot: lane 0 may refill it
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   if (!joints) return;
   __syncthreads();
@@ -713,16 +810,16 @@ extern "C" int hp3d_smpl_lbs(const hp3d_smpl* h, const float* v_posed, const flo
   HP3D_ARG(M > 0 && Mb > 0 && Mg > 0 && M % Mb == 0 && M % Mg == 0, "M must be a multiple of Mb and Mg");
   static int force_generic = -1;
   if (force_generic < 0) { const char* e = getenv("HP3D_LBS"); force_generic = (e && !strcmp(e, "generic")) ? 1 : 0; }
+  static int tile_mode = -1;
+  if (tile_mode < 0) { const char* e = getenv("HP3D_LBS_MODE"); tile_mode = (e && atoi(e) == 2) ? 2 : 4; }
   if (h->tile_nq_max > 0 && !force_generic) {
     const int grid = cdiv(M, LBS_G);
-    if (h->tile_nq_max <= 8)
-      lbs_tile_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M, h->tile_nq,
-                                                                h->tile_joff, h->tile_w, h->reg_rowptr, h->reg_col,
-                                                                h->reg_val, h->pick_ids, h->tree, vertices, joints);
-    else
-      lbs_tile_kernel<NQCAP><<<grid, 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M, h->tile_nq,
-                                                                    h->tile_joff, h->tile_w, h->reg_rowptr, h->reg_col,
-                                                                    h->reg_val, h->pick_ids, h->tree, vertices, joints);
+#define HP3D_LBS_LAUNCH(NQ, MODE)                                                                                     \
+    lbs_tile_kernel<NQ, MODE><<<grid, 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M, \
+        h->tile_nq, h->tile_joff, h->tile_w, h->reg_rowptr, h->reg_col, h->reg_val, h->pick_ids, h->tree, vertices, joints)
+    if (h->tile_nq_max <= 8) { if (tile_mode == 4) HP3D_LBS_LAUNCH(8, 4); else HP3D_LBS_LAUNCH(8, 2); }
+    else { if (tile_mode == 4) HP3D_LBS_LAUNCH(NQCAP, 4); else HP3D_LBS_LAUNCH(NQCAP, 2); }
+#undef HP3D_LBS_LAUNCH
     return launch_status("lbs_tile_kernel");
   }
   const int grid = std::min(M, 148 * 8);
