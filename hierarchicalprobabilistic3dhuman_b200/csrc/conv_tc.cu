@@ -205,13 +205,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // ---------------------------------------------------------------- elementwise helpers (fp16 NHWC)
 __global__ void __launch_bounds__(256) nchw_f32_to_nhwc32_f16_kernel(const float* __restrict__ x, int C, int HW,
                                                                      __half* __restrict__ y) {
-  __shared__ float tile[32][33];
-  const int n = blockIdx.y, p0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int c = ty; c < 32; c += 8) tile[c][tx] = (c < C && p0 + tx < HW) ? x[((size_t)n * C + c) * HW + p0 + tx] : 0.f;
-  __syncthreads();
-  for (int p = ty; p < 32; p += 8)
-    if (p0 + p < HW) y[((size_t)n * HW + p0 + p) * 32 + tx] = __float2half_rn(tile[tx][p]);
+  // thread = (pixel, 16-channel half): 16 (or C-16) coalesced plane reads -> one full 32-byte sector of the
+  // NHWC record (two 16-byte stores); channels >= C are written as zero padding.
+  const int n = blockIdx.y;
+  const int p = blockIdx.x * 128 + (threadIdx.x & 127);
+  const int half_id = threadIdx.x >> 7;               // 0: channels 0..15, 1: channels 16..31
+  if (p >= HW) return;
+  const float* src = x + (size_t)n * C * HW + p;
+  __half2 h[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c0 = half_id * 16 + 2 * k;
+    const float a = (c0 < C) ? src[(size_t)c0 * HW] : 0.f;
+    const float b = (c0 + 1 < C) ? src[(size_t)(c0 + 1) * HW] : 0.f;
+    h[k] = __floats2half2_rn(a, b);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(y + ((size_t)n * HW + p) * 32 + half_id * 16);
+  dst[0] = *reinterpret_cast<const uint4*>(&h[0]);
+  dst[1] = *reinterpret_cast<const uint4*>(&h[4]);
 }
 
 __global__ void __launch_bounds__(256) maxpool3x3s2_f16_kernel(const __half* __restrict__ in, int H, int W, int C, int Ho,
@@ -465,7 +476,7 @@ int encoder_tc_forward(const void* p, const float* x, int B, int H, int W, float
   __half* stem = (__half*)ws; ws += act_bytes(Bp, H / 2, W / 2, 64);
   __half* buf[4];
   for (int i = 0; i < 4; ++i) { buf[i] = (__half*)ws; ws += act_bytes(Bp, H / 4, W / 4, 64); }
-  nchw_f32_to_nhwc32_f16_kernel<<<dim3(cdiv(H * W, 32), B), 256, 0, s>>>(x, 18, H * W, xin);
+  nchw_f32_to_nhwc32_f16_kernel<<<dim3(cdiv(H * W, 128), B), 256, 0, s>>>(x, 18, H * W, xin);
   int rc = launch_status("nchw_f32_to_nhwc32_f16_kernel");
   if (rc) return rc;
   rc = run_tc_conv(E, E->stem, xin, B, H, W, nullptr, 1, stem, s);

@@ -281,7 +281,7 @@ constexpr int LBS_D = 6;                    // bulk-copy ring depth per warp
 constexpr int SLOT_F = 196;                 // floats per ring slot (784 B = 768 + alignment window)
 
 template <int NQMAX, int MODE>   // MODE 2: register prefetch (distance 2), direct 8-byte loads; MODE 4: per-warp TMA bulk-copy ring
-__global__ void __launch_bounds__(256, MODE == 4 ? 3 : 2) lbs_tile_kernel(const float* __restrict__ v_posed, const float* __restrict__ J,
+__global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3) lbs_tile_kernel(const float* __restrict__ v_posed, const float* __restrict__ J,
                                                           int Mb, const float* __restrict__ global_orient, int Mg,
                                                           const float* __restrict__ body_pose, int M,
                                                           const int* __restrict__ tile_nq, const int* __restrict__ tile_joff,
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(256, MODE == 4 ? 3 : 2) lbs_tile_kernel(const 
   // ---- phase 2 (MODE 2): skinning, warp sweeps its tiles, meshes innermost; the two vertices of a lane are
   // loaded/stored with 8-byte accesses straight from/to HBM, the loads of the next two meshes are issued
   // before the current two are skinned (software prefetch, distance 2).
-  if constexpr (MODE == 2) {
+  if constexpr (MODE == 2 || MODE == 5 || MODE == 6) {
     for (int tile = warp; tile < NT; tile += 8) {
       const int nq = tile_nq[tile];
       const int v0 = tile * TV + 2 * lane;
@@ -416,13 +416,23 @@ __global__ void __launch_bounds__(256, MODE == 4 ? 3 : 2) lbs_tile_kernel(const 
           *reinterpret_cast<float2*>(d_ + 4) = o2;
         }
       };
-      ld(0, pa); ld(1, pb);
-      for (int g = 0; g < Gv; g += 2) {
-        ld(g + 2, na); ld(g + 3, nb);
-        skin(g, pa);
-        if (g + 1 < Gv) skin(g + 1, pb);
+      if constexpr (MODE == 6) {          // prefetch distance 1
+        ld(0, pa);
+        for (int g = 0; g < Gv; ++g) {
+          ld(g + 1, na);
+          skin(g, pa);
 #pragma unroll
-        for (int e = 0; e < 3; ++e) { pa[e] = na[e]; pb[e] = nb[e]; }
+          for (int e = 0; e < 3; ++e) pa[e] = na[e];
+        }
+      } else {                            // prefetch distance 2
+        ld(0, pa); ld(1, pb);
+        for (int g = 0; g < Gv; g += 2) {
+          ld(g + 2, na); ld(g + 3, nb);
+          skin(g, pa);
+          if (g + 1 < Gv) skin(g + 1, pb);
+#pragma unroll
+          for (int e = 0; e < 3; ++e) { pa[e] = na[e]; pb[e] = nb[e]; }
+        }
       }
     }
   }
@@ -811,14 +821,17 @@ extern "C" int hp3d_smpl_lbs(const hp3d_smpl* h, const float* v_posed, const flo
   static int force_generic = -1;
   if (force_generic < 0) { const char* e = getenv("HP3D_LBS"); force_generic = (e && !strcmp(e, "generic")) ? 1 : 0; }
   static int tile_mode = -1;
-  if (tile_mode < 0) { const char* e = getenv("HP3D_LBS_MODE"); tile_mode = (e && atoi(e) == 2) ? 2 : 4; }
+  if (tile_mode < 0) { const char* e = getenv("HP3D_LBS_MODE"); tile_mode = e ? atoi(e) : 2; if (tile_mode != 4 && tile_mode != 5 && tile_mode != 6) tile_mode = 2; }
   if (h->tile_nq_max > 0 && !force_generic) {
     const int grid = cdiv(M, LBS_G);
 #define HP3D_LBS_LAUNCH(NQ, MODE)                                                                                     \
     lbs_tile_kernel<NQ, MODE><<<grid, 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M, \
         h->tile_nq, h->tile_joff, h->tile_w, h->reg_rowptr, h->reg_col, h->reg_val, h->pick_ids, h->tree, vertices, joints)
-    if (h->tile_nq_max <= 8) { if (tile_mode == 4) HP3D_LBS_LAUNCH(8, 4); else HP3D_LBS_LAUNCH(8, 2); }
-    else { if (tile_mode == 4) HP3D_LBS_LAUNCH(NQCAP, 4); else HP3D_LBS_LAUNCH(NQCAP, 2); }
+    if (h->tile_nq_max <= 8) {
+      if (tile_mode == 4) HP3D_LBS_LAUNCH(8, 4); else if (tile_mode == 5) HP3D_LBS_LAUNCH(8, 5); else if (tile_mode == 6) HP3D_LBS_LAUNCH(8, 6); else HP3D_LBS_LAUNCH(8, 2);
+    } else {
+      if (tile_mode == 4) HP3D_LBS_LAUNCH(NQCAP, 4); else HP3D_LBS_LAUNCH(NQCAP, 2);
+    }
 #undef HP3D_LBS_LAUNCH
     return launch_status("lbs_tile_kernel");
   }
