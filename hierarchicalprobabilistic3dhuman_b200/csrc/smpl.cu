@@ -44,6 +44,10 @@ struct hp3d_smpl {
   int* tile_nq = nullptr;        // [NT]
   int* tile_joff = nullptr;      // [NT][12]  joint * 3 (float4 units inside one mesh's A block)
   float* tile_w = nullptr;       // [NT][12][64]
+  int* tile_ustart = nullptr;    // [NT+1] per-tile range into tile_uent
+  int* tile_uent = nullptr;      // (vertex_in_tile | slot << 8): vertices the 66 extra joints depend on
+  int* reg_slot = nullptr;       // CSR column -> parked-vertex slot
+  int* pick_slot = nullptr;      // [NPICK]
 };
 
 // ------------------------------------------------------------------ shape blend (K=10, fp32 FFMA)
@@ -264,40 +268,39 @@ __global__ void __launch_bounds__(256) lbs_kernel(const float* __restrict__ v_po
 }
 
 // ------------------------------------------------------------------ fused FK + LBS + joints, tile-local variant
-// The generic kernel above is bound by shared-memory wavefronts: every vertex gathers 4 x 48 B of A
-// with lane-varying addresses (12 LDS.128 = 48 wavefronts per 32 vertices, vs ~33 cycles of HBM time).
-// Skinning weights are spatially coherent (a run of consecutive vertices touches a handful of joints),
-// so at create time each 64-vertex tile gets the list of joints it touches (nq <= 12) and dense
-// per-vertex weights over that list. Then A_{joint q} is a WARP-UNIFORM shared-memory address (broadcast,
-// one wavefront per LDS.128), weights/indices live in registers across the G meshes a CTA owns, and the
-// vertex stream is moved with 8-byte vector loads/stores (2 vertices = 24 B per lane; 82,680 B mesh rows
-// are 8-byte aligned for every mesh). One CTA = G consecutive meshes: warp g runs the FK of mesh g, then
-// the 8 warps sweep the 108 tiles x G meshes, then 66 x G threads-worth of joint regression.
+// The generic kernel above is bound by shared-memory wavefronts: every vertex gathers 4 x 48 B of A with
+// lane-varying addresses (12 LDS.128 = 48 wavefronts per 32 vertices, vs ~33 cycles of HBM time).
+// Skinning weights are spatially coherent (a run of consecutive vertices touches a handful of joints), so at
+// create time each 64-vertex tile gets the list of joints it touches (nq <= 12) and dense per-vertex weights
+// over that list. Then A_{joint q} is a WARP-UNIFORM shared-memory address (broadcast, one wavefront per
+// LDS.128), weights/indices live in registers across the G meshes a CTA owns, and the vertex stream moves with
+// 8-byte vector loads/stores (2 vertices = 24 B per lane; the 82,680-byte mesh rows are 8-byte aligned for
+// every mesh), the loads of the next two meshes being issued before the current two are skinned.
+// One CTA = G = 8 consecutive meshes: warp g runs the FK of mesh g; the 8 warps sweep 108 tiles x G meshes;
+// the <= 276 vertices the 66 extra joints depend on are parked in shared memory as they are produced, so the
+// joint epilogue never re-reads vertices from HBM (they would already have been evicted from L2).
+// History (profiles/README.md): generic 2.02 ms (32 % of HBM peak) -> tile-local 1.09 ms (60 %) -> this.
 constexpr int TV = 64;                      // vertices per tile
 constexpr int NT = (NV + TV - 1) / TV;      // 108
 constexpr int NQCAP = 12;
 constexpr int LBS_G = 8;                    // meshes per CTA (== warps per CTA)
-constexpr int LBS_D = 6;                    // bulk-copy ring depth per warp
-constexpr int SLOT_F = 196;                 // floats per ring slot (784 B = 768 + alignment window)
+constexpr int NU_MAX = NPICK + 255;         // unique vertices feeding the 66 extra joints (<= 276)
 
-template <int NQMAX, int MODE>   // MODE 2: register prefetch (distance 2), direct 8-byte loads; MODE 4: per-warp TMA bulk-copy ring
-__global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3) lbs_tile_kernel(const float* __restrict__ v_posed, const float* __restrict__ J,
+template <int NQMAX>
+__global__ void __launch_bounds__(256, 2) lbs_tile_kernel(const float* __restrict__ v_posed, const float* __restrict__ J,
                                                           int Mb, const float* __restrict__ global_orient, int Mg,
                                                           const float* __restrict__ body_pose, int M,
                                                           const int* __restrict__ tile_nq, const int* __restrict__ tile_joff,
                                                           const float* __restrict__ tile_w,
-                                                          const int* __restrict__ reg_rowptr, const int* __restrict__ reg_col,
-                                                          const float* __restrict__ reg_val, const int* __restrict__ pick_ids,
+                                                          const int* __restrict__ tile_ustart, const int* __restrict__ tile_uent,
+                                                          const int* __restrict__ reg_rowptr, const int* __restrict__ reg_slot,
+                                                          const float* __restrict__ reg_val, const int* __restrict__ pick_slot,
                                                           SmplTree tree, float* __restrict__ vertices,
                                                           float* __restrict__ joints) {
   __shared__ float4 sA[LBS_G][NJ * 3];
-  __shared__ __align__(16) float ring_all[8 * LBS_D * SLOT_F];   // per-warp bulk-copy rings, 784 B slots (phase 2)
-  __shared__ __align__(8) uint64_t ring_bars[8 * LBS_D];
-  float (*sG)[NJ][12] = reinterpret_cast<float (*)[NJ][12]>(ring_all);   // FK scratch (phase 1) aliases the rings
-  if (MODE == 4 && threadIdx.x < 8 * LBS_D) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(ring_bars + threadIdx.x)) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
+  __shared__ float sV[LBS_G][NU_MAX][3];                               // parked vertices for the joint epilogue
+  float (*sG)[NJ][12] = reinterpret_cast<float (*)[NJ][12]>(&sV[0][0][0]);   // FK scratch (phase 1) aliases sV
+  static_assert(sizeof(float) * LBS_G * NJ * 12 <= sizeof(float) * LBS_G * NU_MAX * 3, "FK scratch must fit");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int repb = M / Mb, repg = M / Mg;
   const int m0 = blockIdx.x * LBS_G;
@@ -350,173 +353,46 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3) lbs_tile_kernel(const 
     }
   }
   __syncthreads();
-  // ---- phase 2 (MODE 2): skinning, warp sweeps its tiles, meshes innermost; the two vertices of a lane are
-  // loaded/stored with 8-byte accesses straight from/to HBM, the loads of the next two meshes are issued
-  // before the current two are skinned (software prefetch, distance 2).
-  if constexpr (MODE == 2 || MODE == 5 || MODE == 6) {
-    for (int tile = warp; tile < NT; tile += 8) {
-      const int nq = tile_nq[tile];
-      const int v0 = tile * TV + 2 * lane;
-      const bool valid = v0 < NV;                       // NV is even: a lane's two vertices are both in or out
-      float w0[NQMAX], w1[NQMAX];
-      uint32_t jpack[(NQMAX + 3) / 4];
-#pragma unroll
-      for (int q = 0; q < (NQMAX + 3) / 4; ++q) jpack[q] = 0;
-#pragma unroll
-      for (int q = 0; q < NQMAX; ++q) {
-        w0[q] = 0.f; w1[q] = 0.f;
-        if (q < nq) {
-          const float2 w = *reinterpret_cast<const float2*>(tile_w + ((size_t)tile * NQCAP + q) * TV + 2 * lane);
-          w0[q] = w.x; w1[q] = w.y;
-          jpack[q >> 2] |= (uint32_t)tile_joff[tile * NQCAP + q] << (8 * (q & 3));
-        }
-      }
-      const size_t voff = (size_t)3 * v0;
-      const float* src0 = v_posed + (size_t)m0 * NV3 + voff;
-      float* dst0 = vertices + (size_t)m0 * NV3 + voff;
-      float2 pa[3], pb[3], na[3], nb[3];
-      auto ld = [&](int g, float2 (&p)[3]) {
-        p[0] = p[1] = p[2] = make_float2(0.f, 0.f);
-        if (valid && g < Gv) {
-          const float* s_ = src0 + (size_t)g * NV3;
-          p[0] = *reinterpret_cast<const float2*>(s_);
-          p[1] = *reinterpret_cast<const float2*>(s_ + 2);
-          p[2] = *reinterpret_cast<const float2*>(s_ + 4);
-        }
-      };
-      auto skin = [&](int g, const float2 (&p)[3]) {
-        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, b0 = a0, b1 = a0, b2 = a0;
-        const float4* Ag = sA[g];
-#pragma unroll
-        for (int q = 0; q < NQMAX; ++q) {
-          if (q < nq) {
-            const int jo = (jpack[q >> 2] >> (8 * (q & 3))) & 0xFF;
-            const float4 r0 = Ag[jo], r1 = Ag[jo + 1], r2 = Ag[jo + 2];
-            const float u = w0[q], v = w1[q];
-            a0.x = fmaf(u, r0.x, a0.x); a0.y = fmaf(u, r0.y, a0.y); a0.z = fmaf(u, r0.z, a0.z); a0.w = fmaf(u, r0.w, a0.w);
-            a1.x = fmaf(u, r1.x, a1.x); a1.y = fmaf(u, r1.y, a1.y); a1.z = fmaf(u, r1.z, a1.z); a1.w = fmaf(u, r1.w, a1.w);
-            a2.x = fmaf(u, r2.x, a2.x); a2.y = fmaf(u, r2.y, a2.y); a2.z = fmaf(u, r2.z, a2.z); a2.w = fmaf(u, r2.w, a2.w);
-            b0.x = fmaf(v, r0.x, b0.x); b0.y = fmaf(v, r0.y, b0.y); b0.z = fmaf(v, r0.z, b0.z); b0.w = fmaf(v, r0.w, b0.w);
-            b1.x = fmaf(v, r1.x, b1.x); b1.y = fmaf(v, r1.y, b1.y); b1.z = fmaf(v, r1.z, b1.z); b1.w = fmaf(v, r1.w, b1.w);
-            b2.x = fmaf(v, r2.x, b2.x); b2.y = fmaf(v, r2.y, b2.y); b2.z = fmaf(v, r2.z, b2.z); b2.w = fmaf(v, r2.w, b2.w);
-          }
-        }
-        if (valid) {
-          const float x0 = p[0].x, y0 = p[0].y, z0 = p[1].x, x1 = p[1].y, y1 = p[2].x, z1 = p[2].y;
-          float2 o0, o1, o2;
-          o0.x = fmaf(a0.z, z0, fmaf(a0.y, y0, a0.x * x0)) + a0.w;
-          o0.y = fmaf(a1.z, z0, fmaf(a1.y, y0, a1.x * x0)) + a1.w;
-          o1.x = fmaf(a2.z, z0, fmaf(a2.y, y0, a2.x * x0)) + a2.w;
-          o1.y = fmaf(b0.z, z1, fmaf(b0.y, y1, b0.x * x1)) + b0.w;
-          o2.x = fmaf(b1.z, z1, fmaf(b1.y, y1, b1.x * x1)) + b1.w;
-          o2.y = fmaf(b2.z, z1, fmaf(b2.y, y1, b2.x * x1)) + b2.w;
-          float* d_ = dst0 + (size_t)g * NV3;
-          *reinterpret_cast<float2*>(d_) = o0;
-          *reinterpret_cast<float2*>(d_ + 2) = o1;
-          *reinterpret_cast<float2*>(d_ + 4) = o2;
-        }
-      };
-      if constexpr (MODE == 6) {          // prefetch distance 1
-        ld(0, pa);
-        for (int g = 0; g < Gv; ++g) {
-          ld(g + 1, na);
-          skin(g, pa);
-#pragma unroll
-          for (int e = 0; e < 3; ++e) pa[e] = na[e];
-        }
-      } else {                            // prefetch distance 2
-        ld(0, pa); ld(1, pb);
-        for (int g = 0; g < Gv; g += 2) {
-          ld(g + 2, na); ld(g + 3, nb);
-          skin(g, pa);
-          if (g + 1 < Gv) skin(g + 1, pb);
-#pragma unroll
-          for (int e = 0; e < 3; ++e) { pa[e] = na[e]; pb[e] = nb[e]; }
-        }
-      }
-    }
-  }
-  // ---- phase 2: skinning. Each warp streams its (tile, mesh) items through a private ring of LBS_D
-  // shared-memory slots filled by cp.async (8-byte, fully coalesced: lane l moves bytes [8l, 8l+8) of each
-  // 256-byte third of the 768-byte item), so LBS_D-1 items of HBM latency are in flight per warp without
-  // holding registers; lanes then read "their" two vertices (24 B) back with conflict-free LDS.64, and
-  // results leave through the same slot with coalesced 8-byte stores.
-  // ---- phase 2 (MODE 4): the same skinning, but the vertex stream is staged by the TMA engine: every warp owns a
-  // ring of LBS_D shared-memory slots; lane 0 issues one cp.async.bulk (<= 784 B, 16-byte aligned window around
-  // the 768-byte (tile, mesh) item -- mesh rows are only 8-byte aligned, the window start is rounded down) per item
-  // and an mbarrier per slot signals arrival, so LBS_D-1 items of HBM latency are in flight per warp with no
-  // registers and no LSU instructions spent on the loads.
-  if constexpr (MODE == 4) {
-    float* ring = ring_all + warp * (LBS_D * SLOT_F);
-    uint64_t* bars = ring_bars + warp * LBS_D;
-    const int my_tiles = (NT - warp + 7) / 8;             // tiles warp, warp+8, ...
-    const int n_items = my_tiles * Gv;
-    auto issue = [&](int it) {
-      if (it < n_items && lane == 0) {
-        const int tile = warp + 8 * (it / Gv), g = it - (it / Gv) * Gv;
-        const int nfl = min(TV, NV - tile * TV) * 3;       // floats in this tile (192, last tile 126)
-        const float* src = v_posed + (size_t)(m0 + g) * NV3 + (size_t)tile * (TV * 3);
-        const uintptr_t sa = reinterpret_cast<uintptr_t>(src);
-        const uint32_t shift = (uint32_t)(sa & 15);        // 0 or 8 bytes
-        uint32_t bytes = (shift + (uint32_t)nfl * 4 + 15u) & ~15u;
-        if (bytes > shift + (uint32_t)nfl * 4 && tile == NT - 1 && m0 + g == M - 1) bytes -= 16;   // never read past the buffer
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(ring + (it % LBS_D) * SLOT_F);
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(bars + (it % LBS_D));
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                     "l"(sa - shift), "r"(bytes), "r"(bar) : "memory");
-      }
-    };
-    for (int it = 0; it < LBS_D - 1; ++it) issue(it);
+  // ---- phase 2: skinning, warp sweeps its tiles, meshes innermost
+  for (int tile = warp; tile < NT; tile += 8) {
+    const int nq = tile_nq[tile];
+    const int v0 = tile * TV + 2 * lane;
+    const bool valid = v0 < NV;                       // NV is even: a lane's two vertices are both in or out
     float w0[NQMAX], w1[NQMAX];
     uint32_t jpack[(NQMAX + 3) / 4];
-    int nq = 0;
-    for (int it = 0; it < n_items; ++it) {
-      const int tile = warp + 8 * (it / Gv), g = it - (it / Gv) * Gv;
-      if (g == 0) {                                        // new tile: (re)load its joint list and my two weight columns
-        nq = tile_nq[tile];
 #pragma unroll
-        for (int q = 0; q < (NQMAX + 3) / 4; ++q) jpack[q] = 0;
+    for (int q = 0; q < (NQMAX + 3) / 4; ++q) jpack[q] = 0;
 #pragma unroll
-        for (int q = 0; q < NQMAX; ++q) {
-          w0[q] = 0.f; w1[q] = 0.f;
-          if (q < nq) {
-            const float2 w = *reinterpret_cast<const float2*>(tile_w + ((size_t)tile * NQCAP + q) * TV + 2 * lane);
-            w0[q] = w.x; w1[q] = w.y;
-            jpack[q >> 2] |= (uint32_t)tile_joff[tile * NQCAP + q] << (8 * (q & 3));
-          }
-        }
+    for (int q = 0; q < NQMAX; ++q) {
+      w0[q] = 0.f; w1[q] = 0.f;
+      if (q < nq) {
+        const float2 w = *reinterpret_cast<const float2*>(tile_w + ((size_t)tile * NQCAP + q) * TV + 2 * lane);
+        w0[q] = w.x; w1[q] = w.y;
+        jpack[q >> 2] |= (uint32_t)tile_joff[tile * NQCAP + q] << (8 * (q & 3));
       }
-      issue(it + LBS_D - 1);
-      {   // wait for this item's slot (parity flips every LBS_D items)
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(bars + (it % LBS_D));
-        const uint32_t parity = (uint32_t)((it / LBS_D) & 1);
-        uint32_t ok = 0;
-        long long t0 = 0;
-        while (true) {
-          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-          if (ok) break;
-          if (t0 == 0) t0 = clock64();
-          else if (clock64() - t0 > 4000000000ll) { printf("libhp3d: lbs bulk-copy wait timed out (block %d warp %d item %d)\n", (int)blockIdx.x, warp, it); __trap(); }
-        }
+    }
+    // which of my two vertices feed the joint epilogue, and into which shared-memory slot
+    int park0 = -1, park1 = -1;
+    if (joints) {
+      for (int e = tile_ustart[tile]; e < tile_ustart[tile + 1]; ++e) {
+        const int ent = tile_uent[e], vl = ent & 0xFF, slot = ent >> 8;
+        if ((vl >> 1) == lane) { if (vl & 1) park1 = slot; else park0 = slot; }
       }
-      const float* src = v_posed + (size_t)(m0 + g) * NV3 + (size_t)tile * (TV * 3);
-      const int shift_f = (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 2);   // 0 or 2 floats
-      const float* slot = ring + (it % LBS_D) * SLOT_F + shift_f;
-      const bool valid = tile * TV + 2 * lane < NV;        // NV is even: a lane's two vertices are both in or out
-      float2 p0 = make_float2(0.f, 0.f), p1 = p0, p2 = p0;
-      if (valid) {
-        p0 = *reinterpret_cast<const float2*>(slot + 6 * lane);
-        p1 = *reinterpret_cast<const float2*>(slot + 6 * lane + 2);
-        p2 = *reinterpret_cast<const float2*>(slot + 6 * lane + 4);
-        if (tile == NT - 1 && m0 + g == M - 1 && (6 * lane + 6) * 4 + shift_f * 4 > ((shift_f * 4 + 126 * 4 + 15) & ~15) - 16) {
-          // the very last item of the buffer was clipped by 16 B: fetch the tail directly
-          p0 = *reinterpret_cast<const float2*>(src + 6 * lane);
-          p1 = *reinterpret_cast<const float2*>(src + 6 * lane + 2);
-          p2 = *reinterpret_cast<const float2*>(src + 6 * lane + 4);
-        }
+    }
+    const size_t voff = (size_t)3 * v0;
+    const float* src0 = v_posed + (size_t)m0 * NV3 + voff;
+    float* dst0 = vertices + (size_t)m0 * NV3 + voff;
+    float2 pa[3], pb[3], na[3], nb[3];
+    auto ld = [&](int g, float2 (&p)[3]) {
+      p[0] = p[1] = p[2] = make_float2(0.f, 0.f);
+      if (valid && g < Gv) {
+        const float* s_ = src0 + (size_t)g * NV3;
+        p[0] = *reinterpret_cast<const float2*>(s_);
+        p[1] = *reinterpret_cast<const float2*>(s_ + 2);
+        p[2] = *reinterpret_cast<const float2*>(s_ + 4);
       }
+    };
+    auto skin = [&](int g, const float2 (&p)[3]) {
       float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, b0 = a0, b1 = a0, b2 = a0;
       const float4* Ag = sA[g];
 #pragma unroll
@@ -534,7 +410,7 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3) lbs_tile_kernel(const 
         }
       }
       if (valid) {
-        const float x0 = p0.x, y0 = p0.y, z0 = p1.x, x1 = p1.y, y1 = p2.x, z1 = p2.y;
+        const float x0 = p[0].x, y0 = p[0].y, z0 = p[1].x, x1 = p[1].y, y1 = p[2].x, z1 = p[2].y;
         float2 o0, o1, o2;
         o0.x = fmaf(a0.z, z0, fmaf(a0.y, y0, a0.x * x0)) + a0.w;
         o0.y = fmaf(a1.z, z0, fmaf(a1.y, y0, a1.x * x0)) + a1.w;
@@ -542,30 +418,38 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3) lbs_tile_kernel(const 
         o1.y = fmaf(b0.z, z1, fmaf(b0.y, y1, b0.x * x1)) + b0.w;
         o2.x = fmaf(b1.z, z1, fmaf(b1.y, y1, b1.x * x1)) + b1.w;
         o2.y = fmaf(b2.z, z1, fmaf(b2.y, y1, b2.x * x1)) + b2.w;
-        float* dst = vertices + (size_t)(m0 + g) * NV3 + (size_t)tile * (TV * 3) + 6 * lane;
-        *reinterpret_cast<float2*>(dst) = o0;
-        *reinterpret_cast<float2*>(dst + 2) = o1;
-        *reinterpret_cast<float2*>(dst + 4) = o2;
+        float* d_ = dst0 + (size_t)g * NV3;
+        *reinterpret_cast<float2*>(d_) = o0;
+        *reinterpret_cast<float2*>(d_ + 2) = o1;
+        *reinterpret_cast<float2*>(d_ + 4) = o2;
+        if (park0 >= 0) { sV[g][park0][0] = o0.x; sV[g][park0][1] = o0.y; sV[g][park0][2] = o1.x; }
+        if (park1 >= 0) { sV[g][park1][0] = o1.y; sV[g][park1][1] = o2.x; sV[g][park1][2] = o2.y; }
       }
-      __syncwarp();                                        // every lane has read the slot: lane 0 may refill it
+    };
+    ld(0, pa); ld(1, pb);
+    for (int g = 0; g < Gv; g += 2) {
+      ld(g + 2, na); ld(g + 3, nb);
+      skin(g, pa);
+      if (g + 1 < Gv) skin(g + 1, pb);
+#pragma unroll
+      for (int e = 0; e < 3; ++e) { pa[e] = na[e]; pb[e] = nb[e]; }
     }
   }
   if (!joints) return;
   __syncthreads();
-  // ---- phase 3: picked + regressed joints of the G meshes (vertices re-read through L2)
+  // ---- phase 3: picked + regressed joints of the G meshes from the parked vertices
   for (int it = tid; it < Gv * (NPICK + NREG); it += 256) {
     const int g = it / (NPICK + NREG), r = it - g * (NPICK + NREG);
-    const float* vo = vertices + (size_t)(m0 + g) * NV3;
     float ax = 0.f, ay = 0.f, az = 0.f;
     if (r < NPICK) {
-      const int v = pick_ids[r];
-      ax = __ldcg(vo + 3 * v); ay = __ldcg(vo + 3 * v + 1); az = __ldcg(vo + 3 * v + 2);
+      const int sl = pick_slot[r];
+      ax = sV[g][sl][0]; ay = sV[g][sl][1]; az = sV[g][sl][2];
     } else {
       const int rr = r - NPICK;
       for (int p = reg_rowptr[rr]; p < reg_rowptr[rr + 1]; ++p) {
-        const int v = reg_col[p];
+        const int sl = reg_slot[p];
         const float w = reg_val[p];
-        ax = fmaf(w, __ldcg(vo + 3 * v), ax); ay = fmaf(w, __ldcg(vo + 3 * v + 1), ay); az = fmaf(w, __ldcg(vo + 3 * v + 2), az);
+        ax = fmaf(w, sV[g][sl][0], ax); ay = fmaf(w, sV[g][sl][1], ay); az = fmaf(w, sV[g][sl][2], az);
       }
     }
     float* jo = joints + ((size_t)(m0 + g) * NOUTJ + NJ + r) * 3;
@@ -741,6 +625,31 @@ extern "C" int hp3d_smpl_create(const hp3d_smpl_model* md, hp3d_smpl** out) {
   if (rcol.empty()) { rcol.push_back(0); rval.push_back(0.f); }
   std::vector<int> picks(md->extra_vertex_ids, md->extra_vertex_ids + NPICK);
   for (int p : picks) if (p < 0 || p >= NV) { delete h; set_error("hp3d_smpl_create: extra_vertex_ids out of range"); return -1; }
+  // vertices the joint epilogue needs: unique(pick_ids U regressor columns) -> slots, listed per tile
+  std::vector<int> slot_of(NV, -1), ustart(NT + 1, 0), uent, rslot(rcol.size(), 0), pslot(NPICK, 0);
+  {
+    int nu = 0;
+    for (int v = 0; v < NV; ++v) {
+      bool need = false;
+      for (int p_ : picks) need |= (p_ == v);
+      if (!need) for (size_t e = 0; e < rcol.size() && !need; ++e) need = (rcol[e] == v && rval[e] != 0.f);
+      if (need) slot_of[v] = nu++;
+    }
+    if (nu > NU_MAX) h->tile_nq_max = 0;     // cannot park that many: generic kernel
+    for (int t = 0; t < NT; ++t) {
+      ustart[t] = (int)uent.size();
+      for (int v = t * TV; v < std::min(NV, (t + 1) * TV); ++v)
+        if (slot_of[v] >= 0) uent.push_back((v - t * TV) | (slot_of[v] << 8));
+    }
+    ustart[NT] = (int)uent.size();
+    if (uent.empty()) uent.push_back(0);
+    for (size_t e = 0; e < rcol.size(); ++e) rslot[e] = std::max(0, slot_of[rcol[e]]);
+    for (int p_ = 0; p_ < NPICK; ++p_) pslot[p_] = std::max(0, slot_of[picks[p_]]);
+  }
+  rc = rc ? rc : upload(&h->tile_ustart, ustart.data(), ustart.size());
+  rc = rc ? rc : upload(&h->tile_uent, uent.data(), uent.size());
+  rc = rc ? rc : upload(&h->reg_slot, rslot.data(), rslot.size());
+  rc = rc ? rc : upload(&h->pick_slot, pslot.data(), pslot.size());
   rc = rc ? rc : upload(&h->v_template, vt.data(), vt.size());
   rc = rc ? rc : upload(&h->shapedirs_t, sd.data(), sd.size());
   rc = rc ? rc : upload(&h->posedirs, pd.data(), pd.size());
@@ -767,6 +676,7 @@ extern "C" void hp3d_smpl_destroy(hp3d_smpl* h) {
   cudaFree(h->J_shapedirs); cudaFree(h->skin_idx); cudaFree(h->skin_w); cudaFree(h->reg_rowptr);
   cudaFree(h->reg_col); cudaFree(h->reg_val); cudaFree(h->pick_ids);
   cudaFree(h->tile_nq); cudaFree(h->tile_joff); cudaFree(h->tile_w);
+  cudaFree(h->tile_ustart); cudaFree(h->tile_uent); cudaFree(h->reg_slot); cudaFree(h->pick_slot);
   blend_tc_destroy(h->blend_tc);
   delete h;
 }
@@ -820,19 +730,16 @@ extern "C" int hp3d_smpl_lbs(const hp3d_smpl* h, const float* v_posed, const flo
   HP3D_ARG(M > 0 && Mb > 0 && Mg > 0 && M % Mb == 0 && M % Mg == 0, "M must be a multiple of Mb and Mg");
   static int force_generic = -1;
   if (force_generic < 0) { const char* e = getenv("HP3D_LBS"); force_generic = (e && !strcmp(e, "generic")) ? 1 : 0; }
-  static int tile_mode = -1;
-  if (tile_mode < 0) { const char* e = getenv("HP3D_LBS_MODE"); tile_mode = e ? atoi(e) : 2; if (tile_mode != 4 && tile_mode != 5 && tile_mode != 6) tile_mode = 2; }
   if (h->tile_nq_max > 0 && !force_generic) {
     const int grid = cdiv(M, LBS_G);
-#define HP3D_LBS_LAUNCH(NQ, MODE)                                                                                     \
-    lbs_tile_kernel<NQ, MODE><<<grid, 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M, \
-        h->tile_nq, h->tile_joff, h->tile_w, h->reg_rowptr, h->reg_col, h->reg_val, h->pick_ids, h->tree, vertices, joints)
-    if (h->tile_nq_max <= 8) {
-      if (tile_mode == 4) HP3D_LBS_LAUNCH(8, 4); else if (tile_mode == 5) HP3D_LBS_LAUNCH(8, 5); else if (tile_mode == 6) HP3D_LBS_LAUNCH(8, 6); else HP3D_LBS_LAUNCH(8, 2);
-    } else {
-      if (tile_mode == 4) HP3D_LBS_LAUNCH(NQCAP, 4); else HP3D_LBS_LAUNCH(NQCAP, 2);
-    }
-#undef HP3D_LBS_LAUNCH
+    if (h->tile_nq_max <= 8)
+      lbs_tile_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M, h->tile_nq,
+          h->tile_joff, h->tile_w, h->tile_ustart, h->tile_uent, h->reg_rowptr, h->reg_slot, h->reg_val, h->pick_slot, h->tree,
+          vertices, joints);
+    else
+      lbs_tile_kernel<NQCAP><<<grid, 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M, h->tile_nq,
+          h->tile_joff, h->tile_w, h->tile_ustart, h->tile_uent, h->reg_rowptr, h->reg_slot, h->reg_val, h->pick_slot, h->tree,
+          vertices, joints);
     return launch_status("lbs_tile_kernel");
   }
   const int grid = std::min(M, 148 * 8);
