@@ -286,6 +286,83 @@ constexpr int NQCAP = 12;
 constexpr int LBS_G = 8;                    // meshes per CTA (== warps per CTA)
 constexpr int NU_MAX = NPICK + 255;         // unique vertices feeding the 66 extra joints (<= 276)
 
+struct LbsTileCtx {
+  int tile, lane, m0, Gv, park0, park1;
+  const float* v_posed; float* vertices;
+  const int* tile_joff; const float* tile_w;
+  const float4* sA;     // [LBS_G][NJ*3]
+  float* sV;            // [LBS_G][NU_MAX][3]
+};
+
+// One 64-vertex tile x Gv meshes with exactly NQ joints (compile-time): no per-joint predicates or branches.
+template <int NQ>
+__device__ __forceinline__ void lbs_tile_body(const LbsTileCtx& c) {
+  const int lane = c.lane, tile = c.tile;
+  const int v0 = tile * TV + 2 * lane;
+  const bool valid = v0 < NV;                         // NV is even: a lane's two vertices are both in or out
+  float w0[NQ], w1[NQ];
+  int joff[NQ];                                       // float4 offset of joint q inside one mesh's A block
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const float2 w = *reinterpret_cast<const float2*>(c.tile_w + ((size_t)tile * NQCAP + q) * TV + 2 * lane);
+    w0[q] = w.x; w1[q] = w.y;
+    joff[q] = c.tile_joff[tile * NQCAP + q];
+  }
+  const size_t voff = (size_t)3 * v0;
+  const float* src0 = c.v_posed + (size_t)c.m0 * NV3 + voff;
+  float* dst0 = c.vertices + (size_t)c.m0 * NV3 + voff;
+  const int Gv = c.Gv;
+  float2 pa[3], pb[3], na[3], nb[3];
+  auto ld = [&](int g, float2 (&p)[3]) {
+    p[0] = p[1] = p[2] = make_float2(0.f, 0.f);
+    if (valid && g < Gv) {
+      const float* s_ = src0 + (size_t)g * NV3;
+      p[0] = *reinterpret_cast<const float2*>(s_);
+      p[1] = *reinterpret_cast<const float2*>(s_ + 2);
+      p[2] = *reinterpret_cast<const float2*>(s_ + 4);
+    }
+  };
+  auto skin = [&](int g, const float2 (&p)[3]) {
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, b0 = a0, b1 = a0, b2 = a0;
+    const float4* Ag = c.sA + g * (NJ * 3);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const float4 r0 = Ag[joff[q]], r1 = Ag[joff[q] + 1], r2 = Ag[joff[q] + 2];
+      const float u = w0[q], v = w1[q];
+      a0.x = fmaf(u, r0.x, a0.x); a0.y = fmaf(u, r0.y, a0.y); a0.z = fmaf(u, r0.z, a0.z); a0.w = fmaf(u, r0.w, a0.w);
+      a1.x = fmaf(u, r1.x, a1.x); a1.y = fmaf(u, r1.y, a1.y); a1.z = fmaf(u, r1.z, a1.z); a1.w = fmaf(u, r1.w, a1.w);
+      a2.x = fmaf(u, r2.x, a2.x); a2.y = fmaf(u, r2.y, a2.y); a2.z = fmaf(u, r2.z, a2.z); a2.w = fmaf(u, r2.w, a2.w);
+      b0.x = fmaf(v, r0.x, b0.x); b0.y = fmaf(v, r0.y, b0.y); b0.z = fmaf(v, r0.z, b0.z); b0.w = fmaf(v, r0.w, b0.w);
+      b1.x = fmaf(v, r1.x, b1.x); b1.y = fmaf(v, r1.y, b1.y); b1.z = fmaf(v, r1.z, b1.z); b1.w = fmaf(v, r1.w, b1.w);
+      b2.x = fmaf(v, r2.x, b2.x); b2.y = fmaf(v, r2.y, b2.y); b2.z = fmaf(v, r2.z, b2.z); b2.w = fmaf(v, r2.w, b2.w);
+    }
+    if (valid) {
+      const float x0 = p[0].x, y0 = p[0].y, z0 = p[1].x, x1 = p[1].y, y1 = p[2].x, z1 = p[2].y;
+      float2 o0, o1, o2;
+      o0.x = fmaf(a0.z, z0, fmaf(a0.y, y0, a0.x * x0)) + a0.w;
+      o0.y = fmaf(a1.z, z0, fmaf(a1.y, y0, a1.x * x0)) + a1.w;
+      o1.x = fmaf(a2.z, z0, fmaf(a2.y, y0, a2.x * x0)) + a2.w;
+      o1.y = fmaf(b0.z, z1, fmaf(b0.y, y1, b0.x * x1)) + b0.w;
+      o2.x = fmaf(b1.z, z1, fmaf(b1.y, y1, b1.x * x1)) + b1.w;
+      o2.y = fmaf(b2.z, z1, fmaf(b2.y, y1, b2.x * x1)) + b2.w;
+      float* d_ = dst0 + (size_t)g * NV3;
+      *reinterpret_cast<float2*>(d_) = o0;
+      *reinterpret_cast<float2*>(d_ + 2) = o1;
+      *reinterpret_cast<float2*>(d_ + 4) = o2;
+      if (c.park0 >= 0) { float* sv = c.sV + ((size_t)g * NU_MAX + c.park0) * 3; sv[0] = o0.x; sv[1] = o0.y; sv[2] = o1.x; }
+      if (c.park1 >= 0) { float* sv = c.sV + ((size_t)g * NU_MAX + c.park1) * 3; sv[0] = o1.y; sv[1] = o2.x; sv[2] = o2.y; }
+    }
+  };
+  ld(0, pa); ld(1, pb);
+  for (int g = 0; g < Gv; g += 2) {
+    ld(g + 2, na); ld(g + 3, nb);
+    skin(g, pa);
+    if (g + 1 < Gv) skin(g + 1, pb);
+#pragma unroll
+    for (int e = 0; e < 3; ++e) { pa[e] = na[e]; pb[e] = nb[e]; }
+  }
+}
+
 template <int NQMAX>
 __global__ void __launch_bounds__(256, 2) lbs_tile_kernel(const float* __restrict__ v_posed, const float* __restrict__ J,
                                                           int Mb, const float* __restrict__ global_orient, int Mg,
@@ -353,86 +430,40 @@ __global__ void __launch_bounds__(256, 2) lbs_tile_kernel(const float* __restric
     }
   }
   __syncthreads();
-  // ---- phase 2: skinning, warp sweeps its tiles, meshes innermost
+  // ---- phase 2: skinning, warp sweeps its tiles, meshes innermost. The tile's joint count is warp-uniform:
+  // dispatch once per tile to a fully unrolled, branch-free body for exactly that count.
   for (int tile = warp; tile < NT; tile += 8) {
     const int nq = tile_nq[tile];
-    const int v0 = tile * TV + 2 * lane;
-    const bool valid = v0 < NV;                       // NV is even: a lane's two vertices are both in or out
-    float w0[NQMAX], w1[NQMAX];
-    uint32_t jpack[(NQMAX + 3) / 4];
-#pragma unroll
-    for (int q = 0; q < (NQMAX + 3) / 4; ++q) jpack[q] = 0;
-#pragma unroll
-    for (int q = 0; q < NQMAX; ++q) {
-      w0[q] = 0.f; w1[q] = 0.f;
-      if (q < nq) {
-        const float2 w = *reinterpret_cast<const float2*>(tile_w + ((size_t)tile * NQCAP + q) * TV + 2 * lane);
-        w0[q] = w.x; w1[q] = w.y;
-        jpack[q >> 2] |= (uint32_t)tile_joff[tile * NQCAP + q] << (8 * (q & 3));
-      }
-    }
-    // which of my two vertices feed the joint epilogue, and into which shared-memory slot
-    int park0 = -1, park1 = -1;
-    if (joints) {
+    LbsTileCtx c;
+    c.tile = tile; c.lane = lane; c.m0 = m0; c.Gv = Gv; c.v_posed = v_posed; c.vertices = vertices;
+    c.tile_joff = tile_joff; c.tile_w = tile_w; c.sA = &sA[0][0]; c.sV = &sV[0][0][0];
+    c.park0 = -1; c.park1 = -1;
+    if (joints) {      // which of my two vertices feed the joint epilogue, and into which shared-memory slot
       for (int e = tile_ustart[tile]; e < tile_ustart[tile + 1]; ++e) {
         const int ent = tile_uent[e], vl = ent & 0xFF, slot = ent >> 8;
-        if ((vl >> 1) == lane) { if (vl & 1) park1 = slot; else park0 = slot; }
+        if ((vl >> 1) == lane) { if (vl & 1) c.park1 = slot; else c.park0 = slot; }
       }
     }
-    const size_t voff = (size_t)3 * v0;
-    const float* src0 = v_posed + (size_t)m0 * NV3 + voff;
-    float* dst0 = vertices + (size_t)m0 * NV3 + voff;
-    float2 pa[3], pb[3], na[3], nb[3];
-    auto ld = [&](int g, float2 (&p)[3]) {
-      p[0] = p[1] = p[2] = make_float2(0.f, 0.f);
-      if (valid && g < Gv) {
-        const float* s_ = src0 + (size_t)g * NV3;
-        p[0] = *reinterpret_cast<const float2*>(s_);
-        p[1] = *reinterpret_cast<const float2*>(s_ + 2);
-        p[2] = *reinterpret_cast<const float2*>(s_ + 4);
-      }
-    };
-    auto skin = [&](int g, const float2 (&p)[3]) {
-      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, b0 = a0, b1 = a0, b2 = a0;
-      const float4* Ag = sA[g];
-#pragma unroll
-      for (int q = 0; q < NQMAX; ++q) {
-        if (q < nq) {
-          const int jo = (jpack[q >> 2] >> (8 * (q & 3))) & 0xFF;
-          const float4 r0 = Ag[jo], r1 = Ag[jo + 1], r2 = Ag[jo + 2];
-          const float u = w0[q], v = w1[q];
-          a0.x = fmaf(u, r0.x, a0.x); a0.y = fmaf(u, r0.y, a0.y); a0.z = fmaf(u, r0.z, a0.z); a0.w = fmaf(u, r0.w, a0.w);
-          a1.x = fmaf(u, r1.x, a1.x); a1.y = fmaf(u, r1.y, a1.y); a1.z = fmaf(u, r1.z, a1.z); a1.w = fmaf(u, r1.w, a1.w);
-          a2.x = fmaf(u, r2.x, a2.x); a2.y = fmaf(u, r2.y, a2.y); a2.z = fmaf(u, r2.z, a2.z); a2.w = fmaf(u, r2.w, a2.w);
-          b0.x = fmaf(v, r0.x, b0.x); b0.y = fmaf(v, r0.y, b0.y); b0.z = fmaf(v, r0.z, b0.z); b0.w = fmaf(v, r0.w, b0.w);
-          b1.x = fmaf(v, r1.x, b1.x); b1.y = fmaf(v, r1.y, b1.y); b1.z = fmaf(v, r1.z, b1.z); b1.w = fmaf(v, r1.w, b1.w);
-          b2.x = fmaf(v, r2.x, b2.x); b2.y = fmaf(v, r2.y, b2.y); b2.z = fmaf(v, r2.z, b2.z); b2.w = fmaf(v, r2.w, b2.w);
+    switch (nq) {
+      case 1: lbs_tile_body<1>(c); break;
+      case 2: lbs_tile_body<2>(c); break;
+      case 3: lbs_tile_body<3>(c); break;
+      case 4: lbs_tile_body<4>(c); break;
+      case 5: lbs_tile_body<5>(c); break;
+      case 6: lbs_tile_body<6>(c); break;
+      case 7: lbs_tile_body<7>(c); break;
+      case 8: lbs_tile_body<8>(c); break;
+      default:
+        if constexpr (NQMAX > 8) {
+          switch (nq) {
+            case 9: lbs_tile_body<9>(c); break;
+            case 10: lbs_tile_body<10>(c); break;
+            case 11: lbs_tile_body<11>(c); break;
+            case 12: lbs_tile_body<12>(c); break;
+            default: break;
+          }
         }
-      }
-      if (valid) {
-        const float x0 = p[0].x, y0 = p[0].y, z0 = p[1].x, x1 = p[1].y, y1 = p[2].x, z1 = p[2].y;
-        float2 o0, o1, o2;
-        o0.x = fmaf(a0.z, z0, fmaf(a0.y, y0, a0.x * x0)) + a0.w;
-        o0.y = fmaf(a1.z, z0, fmaf(a1.y, y0, a1.x * x0)) + a1.w;
-        o1.x = fmaf(a2.z, z0, fmaf(a2.y, y0, a2.x * x0)) + a2.w;
-        o1.y = fmaf(b0.z, z1, fmaf(b0.y, y1, b0.x * x1)) + b0.w;
-        o2.x = fmaf(b1.z, z1, fmaf(b1.y, y1, b1.x * x1)) + b1.w;
-        o2.y = fmaf(b2.z, z1, fmaf(b2.y, y1, b2.x * x1)) + b2.w;
-        float* d_ = dst0 + (size_t)g * NV3;
-        *reinterpret_cast<float2*>(d_) = o0;
-        *reinterpret_cast<float2*>(d_ + 2) = o1;
-        *reinterpret_cast<float2*>(d_ + 4) = o2;
-        if (park0 >= 0) { sV[g][park0][0] = o0.x; sV[g][park0][1] = o0.y; sV[g][park0][2] = o1.x; }
-        if (park1 >= 0) { sV[g][park1][0] = o1.y; sV[g][park1][1] = o2.x; sV[g][park1][2] = o2.y; }
-      }
-    };
-    ld(0, pa); ld(1, pb);
-    for (int g = 0; g < Gv; g += 2) {
-      ld(g + 2, na); ld(g + 3, nb);
-      skin(g, pa);
-      if (g + 1 < Gv) skin(g + 1, pb);
-#pragma unroll
-      for (int e = 0; e < 3; ++e) { pa[e] = na[e]; pb[e] = nb[e]; }
+        break;
     }
   }
   if (!joints) return;
