@@ -202,6 +202,206 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   if (warp == 2) { tc_fence_after_sync(); tmem_dealloc<2 * BN>(tmem_base); }
 }
 
+// ---------------------------------------------------------------- halo-patch variant (operand reuse across taps)
+// conv_tc_kernel re-fetches the activation tile once per filter tap (9x for 3x3, 28 k-blocks for the stem): ncu
+// showed those kernels bound by L2->SMEM operand traffic (10.6 TB/s), not by the tensor pipe. Here the input
+// HALO PATCH of an 8(x) x 16(y) output tile is fetched ONCE per 64-channel block, as eight 16-byte-wide planes
+// [py][px][8 ch] (TMA, no swizzle), and every filter tap is a *shifted view* of that patch: with 8 output pixels
+// per row an 8-row core-matrix group is one output row, so group g of the A operand lives at
+// start + g * (PW*16 B) -- exactly the un-swizzled K-major UMMA layout with SBO = PW*16, LBO = plane size.
+// Weights stay 128B-swizzled tiles; they are resident in shared memory when they fit (layer1, 72 KB) and
+// streamed through a ring otherwise. The 7x7/2 stem uses two patches (one per input-row parity).
+constexpr int MAX_TAPS = 28;
+struct PatchArgs {
+  int tiles_m, tiles_n, tiles_x, tiles_y;
+  int N, Ho, Wo, Cout;
+  const float* bias;
+  const __half* residual;
+  __half* out;
+  int relu;
+  int n_cblk, n_taps, n_patch, patch_tx;   // patch_tx: bytes TMA delivers per patch stage
+  int p_pw[2], p_ph[2], p_ox[2], p_oy[2], p_base[2];
+  uint16_t t_off[MAX_TAPS];   // view offset of the tap inside its patch plane, in 16-byte units
+  uint8_t t_patch[MAX_TAPS];
+};
+
+template <int BN, bool RESIDENT, int PS, int BS, int PATCH_STAGE_BYTES, int NKB_RES>
+struct PatchSmem {
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int B_OFFSET = (PS * PATCH_STAGE_BYTES + 1023) / 1024 * 1024;
+  static constexpr int B_REGION = RESIDENT ? NKB_RES * B_BYTES : BS * B_BYTES;
+  static constexpr int BAR_OFFSET = B_OFFSET + B_REGION;
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 512;
+  static constexpr int TOTAL = BIAS_OFFSET + 2 * BN * 4 + 1024;
+};
+
+template <int BN, bool RESIDENT, int PS, int BS, int PATCH_STAGE_BYTES, int NKB_RES>
+__global__ void __launch_bounds__(256, 1)
+conv_patch_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1,
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ PatchArgs args) {
+  using L = PatchSmem<BN, RESIDENT, PS, BS, PATCH_STAGE_BYTES, NKB_RES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* pfull = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* pempty = pfull + PS;
+  uint64_t* bfull = pempty + PS;          // [BS] (streamed) / [1] (resident)
+  uint64_t* bempty = bfull + BS;
+  uint64_t* tmem_full = bempty + BS;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;   // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + L::BIAS_OFFSET);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = args.tiles_m * args.tiles_n;
+  constexpr int BW = 8, BH = 16;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmP0); tma_prefetch_desc(&tmP1); tma_prefetch_desc(&tmB); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < PS; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 1); }
+    for (int s = 0; s < BS; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<2 * BN>(tmem_base_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      if (RESIDENT) {
+        const int nkb = args.n_taps * args.n_cblk;
+        mbar_arrive_expect_tx(&bfull[0], nkb * L::B_BYTES);
+        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem + L::B_OFFSET + kb * L::B_BYTES, &tmB, &bfull[0], kb * BLOCK_K, 0);
+      }
+      int ps = 0, bs = 0; uint32_t pphase = 0, bphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % args.tiles_n, mt = tile / args.tiles_n;
+        const int tx = mt % args.tiles_x, ty = (mt / args.tiles_x) % args.tiles_y;
+        const int n = mt / (args.tiles_x * args.tiles_y);
+        const int ox0 = tx * BW, oy0 = ty * BH;
+        for (int cb = 0; cb < args.n_cblk; ++cb) {
+          mbar_wait(&pempty[ps], pphase ^ 1, 11);
+          mbar_arrive_expect_tx(&pfull[ps], args.patch_tx);
+          uint8_t* stage = smem + ps * PATCH_STAGE_BYTES;
+          for (int p = 0; p < args.n_patch; ++p) {
+            const int plane = (args.p_pw[p] * args.p_ph[p] * 16 + 127) & ~127;   // TMA smem destinations: 128-byte aligned
+            const CUtensorMap* mp = p == 0 ? &tmP0 : &tmP1;
+            for (int j = 0; j < 8; ++j)
+              tma_load_4d(stage + args.p_base[p] + j * plane, mp, &pfull[ps], cb * 64 + 8 * j, ox0 + args.p_ox[p], oy0 + args.p_oy[p], n);
+          }
+          if (++ps == PS) { ps = 0; pphase ^= 1; }
+          if (!RESIDENT) {
+            for (int t = 0; t < args.n_taps; ++t) {
+              mbar_wait(&bempty[bs], bphase ^ 1, 12);
+              mbar_arrive_expect_tx(&bfull[bs], L::B_BYTES);
+              tma_load_2d(smem + L::B_OFFSET + bs * L::B_BYTES, &tmB, &bfull[bs], (t * args.n_cblk + cb) * BLOCK_K, nt * BN);
+              if (++bs == BS) { bs = 0; bphase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BN);
+      int ps = 0, bs = 0; uint32_t pphase = 0, bphase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      const uint32_t b_base = smem_u32(smem + L::B_OFFSET);
+      if (RESIDENT) { mbar_wait(&bfull[0], 0, 13); tc_fence_after_sync(); }
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 2);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int cb = 0; cb < args.n_cblk; ++cb) {
+          mbar_wait(&pfull[ps], pphase, 14);
+          tc_fence_after_sync();
+          const uint32_t stage = smem_u32(smem + ps * PATCH_STAGE_BYTES);
+          for (int t = 0; t < args.n_taps; ++t) {
+            uint32_t b_addr;
+            if (RESIDENT) b_addr = b_base + (uint32_t)((t * args.n_cblk + cb) * L::B_BYTES);
+            else { mbar_wait(&bfull[bs], bphase, 15); tc_fence_after_sync(); b_addr = b_base + (uint32_t)(bs * L::B_BYTES); }
+            const int p = args.t_patch[t];
+            const uint32_t plane = (uint32_t)((args.p_pw[p] * args.p_ph[p] * 16 + 127) & ~127);
+            const uint32_t a_view = stage + (uint32_t)args.p_base[p] + (uint32_t)args.t_off[t] * 16u;
+            const uint32_t sbo = (uint32_t)args.p_pw[p] * 16u;
+            const uint64_t b_desc = umma_desc_sw128(b_addr);
+#pragma unroll
+            for (int j = 0; j < BLOCK_K / 16; ++j)
+              umma_f16(d_tmem, umma_desc_nosw(a_view + (uint32_t)(2 * j) * plane, plane, sbo), b_desc + (uint64_t)(2 * j), idesc,
+                       (cb | t | j) != 0 ? 1u : 0u);
+            if (!RESIDENT) { umma_commit(&bempty[bs]); if (++bs == BS) { bs = 0; bphase ^= 1; } }
+          }
+          umma_commit(&pempty[ps]);
+          if (++ps == PS) { ps = 0; pphase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================================================== epilogue (identical to conv_tc_kernel, BW=8 BH=16)
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    const int et = threadIdx.x - 128;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int nt = tile % args.tiles_n, mt = tile / args.tiles_n;
+      const int tx = mt % args.tiles_x, ty = (mt / args.tiles_x) % args.tiles_y;
+      const int n = mt / (args.tiles_x * args.tiles_y);
+      const int yl = row / BW, xl = row - yl * BW;
+      const size_t pix = ((size_t)n * args.Ho + (ty * BH + yl)) * args.Wo + (tx * BW + xl);
+      const size_t off = pix * args.Cout + (size_t)nt * BN;
+      float* bsm = bias_s + acc * BN;
+      if (et < BN) bsm[et] = args.bias[nt * BN + et];
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&tmem_full[acc], acc_phase, 4);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + ch * 32, r);
+        tmem_ld_wait();
+        const uint4* res = args.residual ? reinterpret_cast<const uint4*>(args.residual + off + ch * 32) : nullptr;
+        uint4* dst = reinterpret_cast<uint4*>(args.out + off + ch * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[q * 8 + e]) + bsm[ch * 32 + q * 8 + e];
+          if (res) {
+            const uint4 rv = res[q];
+            const __half2* h = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+          }
+          if (args.relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+          uint4 o;
+          __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+          dst[q] = o;
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc<2 * BN>(tmem_base); }
+}
+
 // ---------------------------------------------------------------- elementwise helpers (fp16 NHWC)
 __global__ void __launch_bounds__(256) nchw_f32_to_nhwc32_f16_kernel(const float* __restrict__ x, int C, int HW,
                                                                      __half* __restrict__ y) {
@@ -326,8 +526,15 @@ int make_tc_conv(const hp3d_conv_bn& c, float eps, bool stem, TcConv& L) {
 }
 
 // Launch one convolution: in [N][H][W][Cin_mem] fp16 (Cin_mem = 32 for the stem input), out [N][Ho][Wo][Cout].
+int run_patch_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N, int H, int W, const __half* residual,
+                   int relu, __half* out, cudaStream_t s);
+
 int run_tc_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N, int H, int W, const __half* residual,
                 int relu, __half* out, cudaStream_t s) {
+  {
+    const int prc = run_patch_conv(E, L, in, N, H, W, residual, relu, out, s);
+    if (prc != -1000) return prc;  // handled (0) or failed; -1000 = not covered by the patch variant
+  }
   const int Ho = H / L.stride, Wo = W / L.stride;
   const uint64_t Np = (uint64_t)((N + 1) & ~1);   // buffers hold an even number of images (layer4 tiles span two)
   ConvTcArgs a;
@@ -409,6 +616,76 @@ int run_tc_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N, in
     conv_tc_kernel<128, 5><<<grid, 256, SL::TOTAL, s>>>(tmA[0], tmA[1], tmA[2], tmA[3], L.tmB, a);
   }
   return launch_status("conv_tc_kernel");
+}
+
+// Patch-variant launch. Returns PATCH_NOT_COVERED if this layer/geometry is not handled (caller falls back to conv_tc_kernel).
+constexpr int PATCH_NOT_COVERED = -1000;
+template <int BN, bool RESIDENT, int PS, int BS, int PSB, int NKB>
+int launch_patch(const CUtensorMap& p0, const CUtensorMap& p1, const CUtensorMap& b, const PatchArgs& a, int grid, cudaStream_t s) {
+  using SL = PatchSmem<BN, RESIDENT, PS, BS, PSB, NKB>;
+  static_assert(SL::TOTAL <= 232448, "shared memory budget");
+  static bool set = false;
+  if (!set) { HP3D_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, RESIDENT, PS, BS, PSB, NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL)); set = true; }
+  conv_patch_kernel<BN, RESIDENT, PS, BS, PSB, NKB><<<grid, 256, SL::TOTAL, s>>>(p0, p1, b, a);
+  return launch_status("conv_patch_kernel");
+}
+
+constexpr int pad128(int x) { return (x + 127) & ~127; }
+constexpr int PATCH3_BYTES = 8 * pad128(18 * 10 * 16);                           // 3x3/1 halo patch of an 8x16 tile, 64 channels
+constexpr int STEM_PATCH_BYTES = 8 * (pad128(18 * 11 * 16) + pad128(19 * 11 * 16));  // two row-parity patches of pixel pairs
+
+int run_patch_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N, int H, int W, const __half* residual,
+                   int relu, __half* out, cudaStream_t s) {
+  static int disabled = -1;
+  if (disabled < 0) { const char* e = getenv("HP3D_CONV_PATCH"); disabled = (e && !strcmp(e, "0")) ? 1 : 0; }
+  if (disabled) return PATCH_NOT_COVERED;
+  const int Ho = H / L.stride, Wo = W / L.stride;
+  if (Wo % 8 || Ho % 16) return PATCH_NOT_COVERED;
+  const bool generic = !L.stem && L.stride == 1 && L.k == 3 && L.pad == 1 && L.cin % 64 == 0;
+  if (!generic && !L.stem) return PATCH_NOT_COVERED;
+  const uint64_t Np = (uint64_t)((N + 1) & ~1);
+  PatchArgs a;
+  memset(&a, 0, sizeof(a));
+  a.tiles_x = Wo / 8; a.tiles_y = Ho / 16; a.tiles_m = a.tiles_x * a.tiles_y * N; a.tiles_n = L.cout / L.bn;
+  a.N = N; a.Ho = Ho; a.Wo = Wo; a.Cout = L.cout;
+  a.bias = L.bias; a.residual = residual; a.out = out; a.relu = relu;
+  CUtensorMap tmP[2];
+  if (generic) {
+    a.n_cblk = L.cin / 64; a.n_taps = 9; a.n_patch = 1; a.patch_tx = 8 * 18 * 10 * 16;
+    a.p_pw[0] = 10; a.p_ph[0] = 18; a.p_ox[0] = -1; a.p_oy[0] = -1; a.p_base[0] = 0;
+    for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw) { a.t_off[kh * 3 + kw] = (uint16_t)(kh * 10 + kw); a.t_patch[kh * 3 + kw] = 0; }
+    const uint64_t dims[4] = {(uint64_t)L.cin, (uint64_t)W, (uint64_t)H, Np};
+    const uint64_t st[3] = {(uint64_t)L.cin * 2, (uint64_t)W * L.cin * 2, (uint64_t)H * W * L.cin * 2};
+    const uint32_t box[4] = {8, 10, 18, 1};
+    int rc = make_tmap_f16(&tmP[0], in, 4, dims, st, box, false);
+    if (rc) return rc;
+    tmP[1] = tmP[0];
+  } else {   // stem: pixel pairs, two row-parity patches; tap index == weight k-block index = kh*4 + (dp+2)
+    a.n_cblk = 1; a.n_taps = 28; a.n_patch = 2; a.patch_tx = 8 * (18 * 11 + 19 * 11) * 16;
+    // parity 0 rows: kh = 1,3,5 -> dy = -1,0,1 (18 rows); parity 1 rows: kh = 0,2,4,6 -> dy = -2..1 (19 rows)
+    a.p_pw[0] = 11; a.p_ph[0] = 18; a.p_ox[0] = -2; a.p_oy[0] = -1; a.p_base[0] = 0;
+    a.p_pw[1] = 11; a.p_ph[1] = 19; a.p_ox[1] = -2; a.p_oy[1] = -2; a.p_base[1] = 8 * pad128(18 * 11 * 16);
+    for (int kh = 0; kh < 7; ++kh) {
+      const int o = kh - 3, ph = ((o % 2) + 2) % 2, dy = (o - ph) / 2;
+      for (int dp = -2; dp <= 1; ++dp) {
+        const int t = kh * 4 + (dp + 2);
+        a.t_patch[t] = (uint8_t)ph;
+        a.t_off[t] = (uint16_t)((dy - a.p_oy[ph]) * 11 + (dp + 2));
+      }
+    }
+    for (int ph = 0; ph < 2; ++ph) {
+      const uint64_t dims[4] = {64, (uint64_t)W / 2, (uint64_t)H / 2, Np};
+      const uint64_t st[3] = {128, (uint64_t)2 * W * 64, (uint64_t)H * W * 64};
+      const uint32_t box[4] = {8, 11, (uint32_t)a.p_ph[ph], 1};
+      int rc = make_tmap_f16(&tmP[ph], in + (size_t)ph * W * 32, 4, dims, st, box, false);
+      if (rc) return rc;
+    }
+  }
+  const int grid = std::min(a.tiles_m * a.tiles_n, E->num_sms);
+  if (L.stem) return launch_patch<64, false, 2, 8, STEM_PATCH_BYTES, 1>(tmP[0], tmP[1], L.tmB, a, grid, s);
+  if (L.bn == 64 && a.n_cblk == 1) return launch_patch<64, true, 4, 1, PATCH3_BYTES, 9>(tmP[0], tmP[1], L.tmB, a, grid, s);
+  if (L.bn == 128) return launch_patch<128, false, 3, 6, PATCH3_BYTES, 1>(tmP[0], tmP[1], L.tmB, a, grid, s);
+  return PATCH_NOT_COVERED;
 }
 
 size_t act_bytes(int N, int H, int W, int C) { return align_up((size_t)N * H * W * C * 2, 1024); }
