@@ -205,11 +205,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 // ---------------------------------------------------------------- halo-patch variant (operand reuse across taps)
 // conv_tc_kernel re-fetches the activation tile once per filter tap (9x for 3x3, 28 k-blocks for the stem): ncu
 // showed those kernels bound by L2->SMEM operand traffic (10.6 TB/s), not by the tensor pipe. Here the input
-// HALO PATCH of an 8(x) x 16(y) output tile is fetched ONCE per 64-channel block, as eight 16-byte-wide planes
-// [py][px][8 ch] (TMA, no swizzle), and every filter tap is a *shifted view* of that patch: with 8 output pixels
-// per row an 8-row core-matrix group is one output row, so group g of the A operand lives at
-// start + g * (PW*16 B) -- exactly the un-swizzled K-major UMMA layout with SBO = PW*16, LBO = plane size.
-// Weights stay 128B-swizzled tiles; they are resident in shared memory when they fit (layer1, 72 KB) and
+// HALO PATCH of an 8(x) x 16(y) output tile is fetched ONCE per 64-channel block with a single TMA box
+// {64 ch, 16 px, PH rows} (128-byte pixel records, 128B swizzle), and every filter tap is a *shifted view* of that
+// patch: with 8 output pixels per row an 8-row swizzle group is one output row, so group g of the A operand lives at
+// start + g * 2048 B (SBO = patch pitch of 16 pixels) and the tap offset (dy*16 + dx) * 128 B only moves the start
+// address. The 128B swizzle is a function of the absolute shared-memory address bits (the same reason the usual
+// +32 B K-advance inside a swizzle atom works), so TMA-written data and the shifted UMMA view agree.
+// (A first version used eight 16-byte-wide un-swizzled planes per patch: correct, but TMA moves 16-byte box rows
+// far too slowly -- the stem stayed at 2.1 ms.)  Weights stay 128B-swizzled tiles; they are resident in shared memory when they fit (layer1, 72 KB) and
 // streamed through a ring otherwise. The 7x7/2 stem uses two patches (one per input-row parity).
 constexpr int MAX_TAPS = 28;
 struct PatchArgs {
@@ -221,7 +224,7 @@ struct PatchArgs {
   int relu;
   int n_cblk, n_taps, n_patch, patch_tx;   // patch_tx: bytes TMA delivers per patch stage
   int p_pw[2], p_ph[2], p_ox[2], p_oy[2], p_base[2];
-  uint16_t t_off[MAX_TAPS];   // view offset of the tap inside its patch plane, in 16-byte units
+  uint16_t t_off[MAX_TAPS];   // view offset of the tap inside its patch, in pixels (128-byte records)
   uint8_t t_patch[MAX_TAPS];
 };
 
@@ -286,12 +289,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
           mbar_wait(&pempty[ps], pphase ^ 1, 11);
           mbar_arrive_expect_tx(&pfull[ps], args.patch_tx);
           uint8_t* stage = smem + ps * PATCH_STAGE_BYTES;
-          for (int p = 0; p < args.n_patch; ++p) {
-            const int plane = (args.p_pw[p] * args.p_ph[p] * 16 + 127) & ~127;   // TMA smem destinations: 128-byte aligned
-            const CUtensorMap* mp = p == 0 ? &tmP0 : &tmP1;
-            for (int j = 0; j < 8; ++j)
-              tma_load_4d(stage + args.p_base[p] + j * plane, mp, &pfull[ps], cb * 64 + 8 * j, ox0 + args.p_ox[p], oy0 + args.p_oy[p], n);
-          }
+          for (int p = 0; p < args.n_patch; ++p)
+            tma_load_4d(stage + args.p_base[p], p == 0 ? &tmP0 : &tmP1, &pfull[ps], cb * 64, ox0 + args.p_ox[p], oy0 + args.p_oy[p], n);
           if (++ps == PS) { ps = 0; pphase ^= 1; }
           if (!RESIDENT) {
             for (int t = 0; t < args.n_taps; ++t) {
@@ -326,14 +325,12 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
             if (RESIDENT) b_addr = b_base + (uint32_t)((t * args.n_cblk + cb) * L::B_BYTES);
             else { mbar_wait(&bfull[bs], bphase, 15); tc_fence_after_sync(); b_addr = b_base + (uint32_t)(bs * L::B_BYTES); }
             const int p = args.t_patch[t];
-            const uint32_t plane = (uint32_t)((args.p_pw[p] * args.p_ph[p] * 16 + 127) & ~127);
-            const uint32_t a_view = stage + (uint32_t)args.p_base[p] + (uint32_t)args.t_off[t] * 16u;
-            const uint32_t sbo = (uint32_t)args.p_pw[p] * 16u;
+            const uint32_t a_view = stage + (uint32_t)args.p_base[p] + (uint32_t)args.t_off[t] * 128u;
+            const uint64_t a_desc = umma_desc_sw128_sbo(a_view, 16u * 128u);     // 8-row groups are 16 pixels apart
             const uint64_t b_desc = umma_desc_sw128(b_addr);
 #pragma unroll
             for (int j = 0; j < BLOCK_K / 16; ++j)
-              umma_f16(d_tmem, umma_desc_nosw(a_view + (uint32_t)(2 * j) * plane, plane, sbo), b_desc + (uint64_t)(2 * j), idesc,
-                       (cb | t | j) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j), idesc, (cb | t | j) != 0 ? 1u : 0u);
             if (!RESIDENT) { umma_commit(&bempty[bs]); if (++bs == BS) { bs = 0; bphase ^= 1; } }
           }
           umma_commit(&pempty[ps]);
@@ -630,9 +627,9 @@ int launch_patch(const CUtensorMap& p0, const CUtensorMap& p1, const CUtensorMap
   return launch_status("conv_patch_kernel");
 }
 
-constexpr int pad128(int x) { return (x + 127) & ~127; }
-constexpr int PATCH3_BYTES = 8 * pad128(18 * 10 * 16);                           // 3x3/1 halo patch of an 8x16 tile, 64 channels
-constexpr int STEM_PATCH_BYTES = 8 * (pad128(18 * 11 * 16) + pad128(19 * 11 * 16));  // two row-parity patches of pixel pairs
+constexpr int PATCH_PW = 16;                                          // patch pitch in pixels (8 outputs + halo, padded)
+constexpr int PATCH3_BYTES = 18 * PATCH_PW * 128;                     // 3x3/1 halo patch of an 8x16 tile, 64 channels: 36 KB
+constexpr int STEM_PATCH_BYTES = (18 + 19) * PATCH_PW * 128;          // two row-parity patches of pixel pairs: 74 KB
 
 int run_patch_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N, int H, int W, const __half* residual,
                    int relu, __half* out, cudaStream_t s) {
@@ -651,40 +648,40 @@ int run_patch_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N,
   a.bias = L.bias; a.residual = residual; a.out = out; a.relu = relu;
   CUtensorMap tmP[2];
   if (generic) {
-    a.n_cblk = L.cin / 64; a.n_taps = 9; a.n_patch = 1; a.patch_tx = 8 * 18 * 10 * 16;
-    a.p_pw[0] = 10; a.p_ph[0] = 18; a.p_ox[0] = -1; a.p_oy[0] = -1; a.p_base[0] = 0;
-    for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw) { a.t_off[kh * 3 + kw] = (uint16_t)(kh * 10 + kw); a.t_patch[kh * 3 + kw] = 0; }
+    a.n_cblk = L.cin / 64; a.n_taps = 9; a.n_patch = 1; a.patch_tx = PATCH3_BYTES;
+    a.p_pw[0] = PATCH_PW; a.p_ph[0] = 18; a.p_ox[0] = -1; a.p_oy[0] = -1; a.p_base[0] = 0;
+    for (int kh = 0; kh < 3; ++kh) for (int kw = 0; kw < 3; ++kw) { a.t_off[kh * 3 + kw] = (uint16_t)(kh * PATCH_PW + kw); a.t_patch[kh * 3 + kw] = 0; }
     const uint64_t dims[4] = {(uint64_t)L.cin, (uint64_t)W, (uint64_t)H, Np};
     const uint64_t st[3] = {(uint64_t)L.cin * 2, (uint64_t)W * L.cin * 2, (uint64_t)H * W * L.cin * 2};
-    const uint32_t box[4] = {8, 10, 18, 1};
-    int rc = make_tmap_f16(&tmP[0], in, 4, dims, st, box, false);
+    const uint32_t box[4] = {64, PATCH_PW, 18, 1};
+    int rc = make_tmap_f16(&tmP[0], in, 4, dims, st, box, true);
     if (rc) return rc;
     tmP[1] = tmP[0];
   } else {   // stem: pixel pairs, two row-parity patches; tap index == weight k-block index = kh*4 + (dp+2)
-    a.n_cblk = 1; a.n_taps = 28; a.n_patch = 2; a.patch_tx = 8 * (18 * 11 + 19 * 11) * 16;
+    a.n_cblk = 1; a.n_taps = 28; a.n_patch = 2; a.patch_tx = STEM_PATCH_BYTES;
     // parity 0 rows: kh = 1,3,5 -> dy = -1,0,1 (18 rows); parity 1 rows: kh = 0,2,4,6 -> dy = -2..1 (19 rows)
-    a.p_pw[0] = 11; a.p_ph[0] = 18; a.p_ox[0] = -2; a.p_oy[0] = -1; a.p_base[0] = 0;
-    a.p_pw[1] = 11; a.p_ph[1] = 19; a.p_ox[1] = -2; a.p_oy[1] = -2; a.p_base[1] = 8 * pad128(18 * 11 * 16);
+    a.p_pw[0] = PATCH_PW; a.p_ph[0] = 18; a.p_ox[0] = -2; a.p_oy[0] = -1; a.p_base[0] = 0;
+    a.p_pw[1] = PATCH_PW; a.p_ph[1] = 19; a.p_ox[1] = -2; a.p_oy[1] = -2; a.p_base[1] = 18 * PATCH_PW * 128;
     for (int kh = 0; kh < 7; ++kh) {
       const int o = kh - 3, ph = ((o % 2) + 2) % 2, dy = (o - ph) / 2;
       for (int dp = -2; dp <= 1; ++dp) {
         const int t = kh * 4 + (dp + 2);
         a.t_patch[t] = (uint8_t)ph;
-        a.t_off[t] = (uint16_t)((dy - a.p_oy[ph]) * 11 + (dp + 2));
+        a.t_off[t] = (uint16_t)((dy - a.p_oy[ph]) * PATCH_PW + (dp + 2));
       }
     }
     for (int ph = 0; ph < 2; ++ph) {
       const uint64_t dims[4] = {64, (uint64_t)W / 2, (uint64_t)H / 2, Np};
       const uint64_t st[3] = {128, (uint64_t)2 * W * 64, (uint64_t)H * W * 64};
-      const uint32_t box[4] = {8, 11, (uint32_t)a.p_ph[ph], 1};
-      int rc = make_tmap_f16(&tmP[ph], in + (size_t)ph * W * 32, 4, dims, st, box, false);
+      const uint32_t box[4] = {64, PATCH_PW, (uint32_t)a.p_ph[ph], 1};
+      int rc = make_tmap_f16(&tmP[ph], in + (size_t)ph * W * 32, 4, dims, st, box, true);
       if (rc) return rc;
     }
   }
   const int grid = std::min(a.tiles_m * a.tiles_n, E->num_sms);
-  if (L.stem) return launch_patch<64, false, 2, 8, STEM_PATCH_BYTES, 1>(tmP[0], tmP[1], L.tmB, a, grid, s);
-  if (L.bn == 64 && a.n_cblk == 1) return launch_patch<64, true, 4, 1, PATCH3_BYTES, 9>(tmP[0], tmP[1], L.tmB, a, grid, s);
-  if (L.bn == 128) return launch_patch<128, false, 3, 6, PATCH3_BYTES, 1>(tmP[0], tmP[1], L.tmB, a, grid, s);
+  if (L.stem) return launch_patch<64, false, 2, 6, STEM_PATCH_BYTES, 1>(tmP[0], tmP[1], L.tmB, a, grid, s);
+  if (L.bn == 64 && a.n_cblk == 1) return launch_patch<64, true, 3, 1, PATCH3_BYTES, 9>(tmP[0], tmP[1], L.tmB, a, grid, s);
+  if (L.bn == 128) return launch_patch<128, false, 3, 5, PATCH3_BYTES, 1>(tmP[0], tmP[1], L.tmB, a, grid, s);
   return PATCH_NOT_COVERED;
 }
 

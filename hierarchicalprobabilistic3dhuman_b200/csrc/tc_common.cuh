@@ -118,6 +118,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// Same layout with an explicit stride between 8-row groups (`sbo` bytes): used for shifted views of a halo patch.
+__device__ __forceinline__ uint64_t umma_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+}
 // K-major operand WITHOUT swizzle ("interleaved" canonical layout): 8-row x 16-byte core matrices (128 contiguous
 // bytes), `lbo` bytes between the two core matrices of one K=16 step, `sbo` bytes between consecutive 8-row groups.
 // Because the layout is purely linear, any 16-byte-aligned address is a valid start: a shifted *view* of a halo
