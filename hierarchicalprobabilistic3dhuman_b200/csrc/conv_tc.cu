@@ -31,7 +31,7 @@ constexpr int MAX_KB = 72;
 constexpr int BLOCK_M = 128, BLOCK_K = 64;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;   // 16 KB
 
-struct KBlock { int8_t map, dx, dy, pad; int16_t c, pad2; };   // A-tile source of one k-block
+struct KBlock { int8_t map, dx, dy, pad; int16_t c, bk; };     // A-tile source of one k-block + weight block index
 
 struct ConvTcArgs {
   int num_kb;
@@ -46,13 +46,58 @@ struct ConvTcArgs {
   KBlock kb[MAX_KB];
 };
 
+// Epilogue of one 128 x BN accumulator tile, executed by the 4 epilogue warps (thread = TMEM lane = output pixel):
+// the residual (skip connection) is prefetched into registers BEFORE waiting for the accumulator so its HBM/L2
+// latency hides behind the MMAs of this tile; bias comes from a CTA-resident shared-memory copy.
+template <int BN>
+__device__ __forceinline__ void conv_epilogue_tile(uint32_t taddr, const float* __restrict__ bias_s, const __half* __restrict__ residual,
+                                                   __half* __restrict__ out, size_t off, bool store, int relu,
+                                                   uint64_t* tmem_full_bar, uint32_t parity) {
+  uint4 rv[BN / 8];
+  if (residual && store) {
+#pragma unroll
+    for (int q = 0; q < BN / 8; ++q) rv[q] = reinterpret_cast<const uint4*>(residual + off)[q];
+  }
+  mbar_wait(tmem_full_bar, parity, 4);
+  tc_fence_after_sync();
+#pragma unroll
+  for (int ch = 0; ch < BN / 32; ++ch) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + ch * 32, r);
+    tmem_ld_wait();
+    if (store) {
+      uint4* dst = reinterpret_cast<uint4*>(out + off + ch * 32);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[q * 8 + e]) + bias_s[ch * 32 + q * 8 + e];
+        if (residual) {
+          const __half2* h = reinterpret_cast<const __half2*>(&rv[ch * 4 + q]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
+        }
+        if (relu) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+        }
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        dst[q] = o;
+      }
+    }
+  }
+}
+
 template <int BN, int STAGES>
 struct SmemLayout {
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int BIAS_OFFSET = BAR_OFFSET + 256;
-  static constexpr int TOTAL = BIAS_OFFSET + 2 * BN * 4 + 1024;   // + slack for 1024-byte alignment
+  static constexpr int TOTAL = BIAS_OFFSET + 512 * 4 + 1024;      // bias (Cout <= 512) + slack for 1024-byte alignment
 };
 
 template <int BN, int STAGES>
@@ -91,7 +136,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
+    {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int nt = tile % args.tiles_n, mt = tile / args.tiles_n;
@@ -102,11 +147,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
           uint8_t* a_dst = smem + stage * L::STAGE_BYTES;
           uint8_t* b_dst = a_dst + A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          if (elect_one()) mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           const KBlock k = args.kb[kb];
           const CUtensorMap* ma = (k.map == 0) ? &tmA0 : (k.map == 1) ? &tmA1 : (k.map == 2) ? &tmA2 : &tmA3;
-          tma_load_4d(a_dst, ma, &full_bar[stage], k.c, ox0 + k.dx, oy0 + k.dy, n0);
-          tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BLOCK_K, nt * BN);
+          if (elect_one()) tma_load_4d(a_dst, ma, &full_bar[stage], k.c, ox0 + k.dx, oy0 + k.dy, n0);
+          if (elect_one()) tma_load_3d(b_dst, &tmB, &full_bar[stage], 0, nt * BN, k.bk);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -114,7 +159,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================== MMA issuer (single thread)
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_f16(BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -130,9 +175,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const uint64_t b_desc = umma_desc_sw128(a_addr + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k)
-            umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);                       // frees the smem slot when these MMAs retire
-          if (kb == args.num_kb - 1) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
+            if (elect_one()) umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          if (elect_one()) umma_commit(&empty_bar[stage]);                       // frees the smem slot when these MMAs retire
+          if (kb == args.num_kb - 1) if (elect_one()) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -146,6 +191,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int et = threadIdx.x - 128;
     int acc = 0; uint32_t acc_phase = 0;
     const int img_px = args.BW * args.BH;
+    for (int c = et; c < args.Cout; c += 128) bias_s[c] = args.bias[c];          // whole bias vector, once per CTA
+    asm volatile("bar.sync 1, 128;" ::: "memory");                               // epilogue-only named barrier
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int nt = tile % args.tiles_n, mt = tile / args.tiles_n;
       const int tx = mt % args.tiles_x, ty = (mt / args.tiles_x) % args.tiles_y;
@@ -155,43 +202,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int n = n0 + il;
       const size_t pix = ((size_t)n * args.Ho + (ty * args.BH + yl)) * args.Wo + (tx * args.BW + xl);
       const size_t off = pix * args.Cout + (size_t)nt * BN;
-      float* bsm = bias_s + acc * BN;
-      if (et < BN) bsm[et] = args.bias[nt * BN + et];
-      asm volatile("bar.sync 1, 128;" ::: "memory");            // epilogue-only named barrier
-      mbar_wait(&tmem_full[acc], acc_phase, 4);
-      tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + ch * 32, r);
-        tmem_ld_wait();
-        if (n < args.N) {
-          const uint4* res = args.residual ? reinterpret_cast<const uint4*>(args.residual + off + ch * 32) : nullptr;
-          uint4* dst = reinterpret_cast<uint4*>(args.out + off + ch * 32);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[q * 8 + e]) + bsm[ch * 32 + q * 8 + e];
-            if (res) {
-              const uint4 rv = res[q];
-              const __half2* h = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
-            }
-            if (args.relu) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-            }
-            uint4 o;
-            __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-            dst[q] = o;
-          }
-        }
-      }
+      conv_epilogue_tile<BN>(taddr, bias_s + nt * BN, args.residual, args.out, off, n < args.N, args.relu, &tmem_full[acc], acc_phase);
       tc_fence_before_sync();
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -223,26 +235,28 @@ struct PatchArgs {
   __half* out;
   int relu;
   int n_cblk, n_taps, n_patch, patch_tx;   // patch_tx: bytes TMA delivers per patch stage
+  int debug;                               // timing experiments only (HP3D_CONV_DEBUG): 1 no stores, 2 no MMAs, 4 no TMA
   int p_pw[2], p_ph[2], p_ox[2], p_oy[2], p_base[2];
   uint16_t t_off[MAX_TAPS];   // view offset of the tap inside its patch, in pixels (128-byte records)
   uint8_t t_patch[MAX_TAPS];
 };
 
-template <int BN, bool RESIDENT, int PS, int BS, int PATCH_STAGE_BYTES, int NKB_RES>
+template <int BN, bool RESIDENT, int PS, int BS, int PATCH_STAGE_BYTES, int NKB_RES, int TPS>
 struct PatchSmem {
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int BSTAGE_BYTES = TPS * B_BYTES;          // one ring stage = TPS consecutive taps, ONE TMA box
   static constexpr int B_OFFSET = (PS * PATCH_STAGE_BYTES + 1023) / 1024 * 1024;
-  static constexpr int B_REGION = RESIDENT ? NKB_RES * B_BYTES : BS * B_BYTES;
+  static constexpr int B_REGION = RESIDENT ? NKB_RES * B_BYTES : BS * BSTAGE_BYTES;
   static constexpr int BAR_OFFSET = B_OFFSET + B_REGION;
   static constexpr int BIAS_OFFSET = BAR_OFFSET + 512;
-  static constexpr int TOTAL = BIAS_OFFSET + 2 * BN * 4 + 1024;
+  static constexpr int TOTAL = BIAS_OFFSET + 512 * 4 + 1024;
 };
 
-template <int BN, bool RESIDENT, int PS, int BS, int PATCH_STAGE_BYTES, int NKB_RES>
+template <int BN, bool RESIDENT, int PS, int BS, int PATCH_STAGE_BYTES, int NKB_RES, int TPS>
 __global__ void __launch_bounds__(256, 1)
 conv_patch_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ PatchArgs args) {
-  using L = PatchSmem<BN, RESIDENT, PS, BS, PATCH_STAGE_BYTES, NKB_RES>;
+  using L = PatchSmem<BN, RESIDENT, PS, BS, PATCH_STAGE_BYTES, NKB_RES, TPS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* pfull = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -273,11 +287,11 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
+    {
       if (RESIDENT) {
         const int nkb = args.n_taps * args.n_cblk;
-        mbar_arrive_expect_tx(&bfull[0], nkb * L::B_BYTES);
-        for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smem + L::B_OFFSET + kb * L::B_BYTES, &tmB, &bfull[0], kb * BLOCK_K, 0);
+        if (elect_one()) mbar_arrive_expect_tx(&bfull[0], nkb * L::B_BYTES);
+        if (elect_one()) tma_load_3d(smem + L::B_OFFSET, &tmB, &bfull[0], 0, 0, 0);     // the whole weight tensor: one box
       }
       int ps = 0, bs = 0; uint32_t pphase = 0, bphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -287,16 +301,22 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
         const int ox0 = tx * BW, oy0 = ty * BH;
         for (int cb = 0; cb < args.n_cblk; ++cb) {
           mbar_wait(&pempty[ps], pphase ^ 1, 11);
-          mbar_arrive_expect_tx(&pfull[ps], args.patch_tx);
           uint8_t* stage = smem + ps * PATCH_STAGE_BYTES;
-          for (int p = 0; p < args.n_patch; ++p)
-            tma_load_4d(stage + args.p_base[p], p == 0 ? &tmP0 : &tmP1, &pfull[ps], cb * 64, ox0 + args.p_ox[p], oy0 + args.p_oy[p], n);
+          if (args.debug & 4) { if (elect_one()) mbar_arrive(&pfull[ps]); }
+          else {
+            if (elect_one()) mbar_arrive_expect_tx(&pfull[ps], args.patch_tx);
+            for (int p = 0; p < args.n_patch; ++p)
+              if (elect_one()) tma_load_4d(stage + args.p_base[p], p == 0 ? &tmP0 : &tmP1, &pfull[ps], cb * 64, ox0 + args.p_ox[p], oy0 + args.p_oy[p], n);
+          }
           if (++ps == PS) { ps = 0; pphase ^= 1; }
           if (!RESIDENT) {
-            for (int t = 0; t < args.n_taps; ++t) {
+            for (int t = 0; t < args.n_taps; t += TPS) {
               mbar_wait(&bempty[bs], bphase ^ 1, 12);
-              mbar_arrive_expect_tx(&bfull[bs], L::B_BYTES);
-              tma_load_2d(smem + L::B_OFFSET + bs * L::B_BYTES, &tmB, &bfull[bs], (t * args.n_cblk + cb) * BLOCK_K, nt * BN);
+              if (args.debug & 4) { if (elect_one()) mbar_arrive(&bfull[bs]); }
+              else {
+                if (elect_one()) mbar_arrive_expect_tx(&bfull[bs], L::BSTAGE_BYTES);
+                if (elect_one()) tma_load_3d(smem + L::B_OFFSET + bs * L::BSTAGE_BYTES, &tmB, &bfull[bs], 0, nt * BN, cb * args.n_taps + t);
+              }
               if (++bs == BS) { bs = 0; bphase ^= 1; }
             }
           }
@@ -306,7 +326,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_f16(BN);
       int ps = 0, bs = 0; uint32_t pphase = 0, bphase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -322,21 +342,26 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
           const uint32_t stage = smem_u32(smem + ps * PATCH_STAGE_BYTES);
           for (int t = 0; t < args.n_taps; ++t) {
             uint32_t b_addr;
-            if (RESIDENT) b_addr = b_base + (uint32_t)((t * args.n_cblk + cb) * L::B_BYTES);
-            else { mbar_wait(&bfull[bs], bphase, 15); tc_fence_after_sync(); b_addr = b_base + (uint32_t)(bs * L::B_BYTES); }
+            if (RESIDENT) b_addr = b_base + (uint32_t)((cb * args.n_taps + t) * L::B_BYTES);
+            else {
+              if (t % TPS == 0) { mbar_wait(&bfull[bs], bphase, 15); tc_fence_after_sync(); }
+              b_addr = b_base + (uint32_t)(bs * L::BSTAGE_BYTES + (t % TPS) * L::B_BYTES);
+            }
             const int p = args.t_patch[t];
             const uint32_t a_view = stage + (uint32_t)args.p_base[p] + (uint32_t)args.t_off[t] * 128u;
             const uint64_t a_desc = umma_desc_sw128_sbo(a_view, 16u * 128u);     // 8-row groups are 16 pixels apart
             const uint64_t b_desc = umma_desc_sw128(b_addr);
+            if (!(args.debug & 2)) {
 #pragma unroll
-            for (int j = 0; j < BLOCK_K / 16; ++j)
-              umma_f16(d_tmem, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j), idesc, (cb | t | j) != 0 ? 1u : 0u);
-            if (!RESIDENT) { umma_commit(&bempty[bs]); if (++bs == BS) { bs = 0; bphase ^= 1; } }
+              for (int j = 0; j < BLOCK_K / 16; ++j)
+                if (elect_one()) umma_f16(d_tmem, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j), idesc, (cb | t | j) != 0 ? 1u : 0u);
+            }
+            if (!RESIDENT && (t % TPS) == TPS - 1) { if (elect_one()) umma_commit(&bempty[bs]); if (++bs == BS) { bs = 0; bphase ^= 1; } }
           }
-          umma_commit(&pempty[ps]);
+          if (elect_one()) umma_commit(&pempty[ps]);
           if (++ps == PS) { ps = 0; pphase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
+        if (elect_one()) umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -347,6 +372,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
     const int row = ew * 32 + lane;
     const int et = threadIdx.x - 128;
     int acc = 0; uint32_t acc_phase = 0;
+    for (int c = et; c < args.Cout; c += 128) bias_s[c] = args.bias[c];
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int nt = tile % args.tiles_n, mt = tile / args.tiles_n;
       const int tx = mt % args.tiles_x, ty = (mt / args.tiles_x) % args.tiles_y;
@@ -354,41 +381,8 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
       const int yl = row / BW, xl = row - yl * BW;
       const size_t pix = ((size_t)n * args.Ho + (ty * BH + yl)) * args.Wo + (tx * BW + xl);
       const size_t off = pix * args.Cout + (size_t)nt * BN;
-      float* bsm = bias_s + acc * BN;
-      if (et < BN) bsm[et] = args.bias[nt * BN + et];
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(&tmem_full[acc], acc_phase, 4);
-      tc_fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + ch * 32, r);
-        tmem_ld_wait();
-        const uint4* res = args.residual ? reinterpret_cast<const uint4*>(args.residual + off + ch * 32) : nullptr;
-        uint4* dst = reinterpret_cast<uint4*>(args.out + off + ch * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[q * 8 + e]) + bsm[ch * 32 + q * 8 + e];
-          if (res) {
-            const uint4 rv = res[q];
-            const __half2* h = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { const float2 f = __half22float2(h[e]); v[2 * e] += f.x; v[2 * e + 1] += f.y; }
-          }
-          if (args.relu) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-          }
-          uint4 o;
-          __half2* oh = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-          dst[q] = o;
-        }
-      }
+      conv_epilogue_tile<BN>(taddr, bias_s + nt * BN, args.residual, args.out, off, !(args.debug & 1), args.relu, &tmem_full[acc], acc_phase);
       tc_fence_before_sync();
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -483,6 +477,14 @@ struct EncoderTc {
   int num_sms = 148;
 };
 
+// 3-D tensor map over the blocked weights {64, Cout, n_kblocks}; one box = `kb_per_box` k-blocks of BN channels.
+int make_weight_tmap(const TcConv& L, int kb_per_box, CUtensorMap* out) {
+  const uint64_t dims[3] = {64, (uint64_t)L.cout, (uint64_t)(L.ktot / 64)};
+  const uint64_t strides[2] = {128, (uint64_t)L.cout * 128};
+  const uint32_t box[3] = {64, (uint32_t)L.bn, (uint32_t)kb_per_box};
+  return make_tmap_f16(out, L.w, 3, dims, strides, box);
+}
+
 int make_tc_conv(const hp3d_conv_bn& c, float eps, bool stem, TcConv& L) {
   std::vector<float> w_khwc, bias;
   // fold BN in fp64, layout [kh][kw][cin][cout]
@@ -490,16 +492,21 @@ int make_tc_conv(const hp3d_conv_bn& c, float eps, bool stem, TcConv& L) {
   if (rc) return rc;
   L.cin = c.cin; L.cout = c.cout; L.k = c.k; L.stride = c.stride; L.pad = c.pad; L.stem = stem;
   L.bn = (c.cout == 64) ? 64 : 128;
+  // blocked layout [kbm][Cout][64]: one 128-byte row per (k-block, output channel); k-blocks are ordered
+  // channel-block major, tap minor (kbm = cb * ntaps + tap) so the taps of one channel block are contiguous and a
+  // group of them is a single 3-D TMA box.
   std::vector<__half> wk;
   if (!stem) {
-    L.ktot = c.k * c.k * c.cin;                       // K index = (kh*k + kw)*cin + ci
-    wk.resize((size_t)c.cout * L.ktot);
-    for (int o = 0; o < c.cout; ++o)
-      for (int t = 0; t < c.k * c.k; ++t)
-        for (int i = 0; i < c.cin; ++i)
-          wk[(size_t)o * L.ktot + (size_t)t * c.cin + i] = __float2half_rn(w_khwc[((size_t)t * c.cin + i) * c.cout + o]);
+    L.ktot = c.k * c.k * c.cin;
+    const int ntaps = c.k * c.k, ncb = c.cin / 64;
+    wk.assign((size_t)c.cout * L.ktot, __float2half_rn(0.f));
+    for (int cb = 0; cb < ncb; ++cb)
+      for (int t = 0; t < ntaps; ++t)
+        for (int o = 0; o < c.cout; ++o)
+          for (int i = 0; i < 64; ++i)
+            wk[(((size_t)cb * ntaps + t) * c.cout + o) * 64 + i] = __float2half_rn(w_khwc[((size_t)t * c.cin + cb * 64 + i) * c.cout + o]);
   } else {
-    // K index = kh*256 + (dp+2)*64 + e*32 + ci with input column 2(x+dp)+e = 2x + kw - 3  =>  kw = 2dp + e + 3
+    // k-block = kh*4 + (dp+2); inside it e*32 + ci with input column 2(x+dp)+e = 2x + kw - 3  =>  kw = 2dp + e + 3
     L.ktot = 7 * 256;
     wk.assign((size_t)c.cout * L.ktot, __float2half_rn(0.f));
     for (int o = 0; o < c.cout; ++o)
@@ -509,17 +516,14 @@ int make_tc_conv(const hp3d_conv_bn& c, float eps, bool stem, TcConv& L) {
             const int kw = 2 * dp + e + 3;
             if (kw < 0 || kw > 6) continue;
             for (int i = 0; i < c.cin; ++i)
-              wk[(size_t)o * L.ktot + kh * 256 + (dp + 2) * 64 + e * 32 + i] =
+              wk[(((size_t)kh * 4 + (dp + 2)) * c.cout + o) * 64 + e * 32 + i] =
                   __float2half_rn(w_khwc[(((size_t)kh * 7 + kw) * c.cin + i) * c.cout + o]);
           }
   }
   rc = upload(&L.w, wk.data(), wk.size());
   rc = rc ? rc : upload(&L.bias, bias.data(), bias.size());
   if (rc) return rc;
-  const uint64_t dims[2] = {(uint64_t)L.ktot, (uint64_t)L.cout};
-  const uint64_t strides[1] = {(uint64_t)L.ktot * 2};
-  const uint32_t box[2] = {64, (uint32_t)L.bn};
-  return make_tmap_f16(&L.tmB, L.w, 2, dims, strides, box);
+  return make_weight_tmap(L, 1, &L.tmB);
 }
 
 // Launch one convolution: in [N][H][W][Cin_mem] fp16 (Cin_mem = 32 for the stem input), out [N][Ho][Wo][Cout].
@@ -563,7 +567,7 @@ int run_tc_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N, in
       const int dy = (o - ph) / 2;
       for (int dp = -2; dp <= 1; ++dp) {
         KBlock& k = a.kb[nk++];
-        k.map = (int8_t)ph; k.dx = (int8_t)dp; k.dy = (int8_t)dy; k.c = 0;
+        k.map = (int8_t)ph; k.dx = (int8_t)dp; k.dy = (int8_t)dy; k.c = 0; k.bk = (int16_t)(kh * 4 + (dp + 2));
       }
     }
   } else if (L.stride == 1) {
@@ -577,6 +581,7 @@ int run_tc_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N, in
         for (int c = 0; c < L.cin; c += 64) {
           KBlock& k = a.kb[nk++];
           k.map = 0; k.dx = (int8_t)(kw - L.pad); k.dy = (int8_t)(kh - L.pad); k.c = (int16_t)c;
+          k.bk = (int16_t)((c / 64) * (L.k * L.k) + kh * L.k + kw);
         }
   } else {   // stride 2: parity maps, map index = py*2 + px
     for (int py = 0; py < 2; ++py)
@@ -594,6 +599,7 @@ int run_tc_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N, in
         for (int c = 0; c < L.cin; c += 64) {
           KBlock& k = a.kb[nk++];
           k.map = (int8_t)(py * 2 + px); k.dx = (int8_t)((ox - px) / 2); k.dy = (int8_t)((oy - py) / 2); k.c = (int16_t)c;
+          k.bk = (int16_t)((c / 64) * (L.k * L.k) + kh * L.k + kw);
         }
       }
   }
@@ -617,13 +623,13 @@ int run_tc_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N, in
 
 // Patch-variant launch. Returns PATCH_NOT_COVERED if this layer/geometry is not handled (caller falls back to conv_tc_kernel).
 constexpr int PATCH_NOT_COVERED = -1000;
-template <int BN, bool RESIDENT, int PS, int BS, int PSB, int NKB>
+template <int BN, bool RESIDENT, int PS, int BS, int PSB, int NKB, int TPS>
 int launch_patch(const CUtensorMap& p0, const CUtensorMap& p1, const CUtensorMap& b, const PatchArgs& a, int grid, cudaStream_t s) {
-  using SL = PatchSmem<BN, RESIDENT, PS, BS, PSB, NKB>;
+  using SL = PatchSmem<BN, RESIDENT, PS, BS, PSB, NKB, TPS>;
   static_assert(SL::TOTAL <= 232448, "shared memory budget");
   static bool set = false;
-  if (!set) { HP3D_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, RESIDENT, PS, BS, PSB, NKB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL)); set = true; }
-  conv_patch_kernel<BN, RESIDENT, PS, BS, PSB, NKB><<<grid, 256, SL::TOTAL, s>>>(p0, p1, b, a);
+  if (!set) { HP3D_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, RESIDENT, PS, BS, PSB, NKB, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL)); set = true; }
+  conv_patch_kernel<BN, RESIDENT, PS, BS, PSB, NKB, TPS><<<grid, 256, SL::TOTAL, s>>>(p0, p1, b, a);
   return launch_status("conv_patch_kernel");
 }
 
@@ -646,6 +652,7 @@ int run_patch_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N,
   a.tiles_x = Wo / 8; a.tiles_y = Ho / 16; a.tiles_m = a.tiles_x * a.tiles_y * N; a.tiles_n = L.cout / L.bn;
   a.N = N; a.Ho = Ho; a.Wo = Wo; a.Cout = L.cout;
   a.bias = L.bias; a.residual = residual; a.out = out; a.relu = relu;
+  { const char* e = getenv("HP3D_CONV_DEBUG"); a.debug = e ? atoi(e) : 0; }
   CUtensorMap tmP[2];
   if (generic) {
     a.n_cblk = L.cin / 64; a.n_taps = 9; a.n_patch = 1; a.patch_tx = PATCH3_BYTES;
@@ -679,9 +686,19 @@ int run_patch_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N,
     }
   }
   const int grid = std::min(a.tiles_m * a.tiles_n, E->num_sms);
-  if (L.stem) return launch_patch<64, false, 2, 6, STEM_PATCH_BYTES, 1>(tmP[0], tmP[1], L.tmB, a, grid, s);
-  if (L.bn == 64 && a.n_cblk == 1) return launch_patch<64, true, 3, 1, PATCH3_BYTES, 9>(tmP[0], tmP[1], L.tmB, a, grid, s);
-  if (L.bn == 128) return launch_patch<128, false, 3, 5, PATCH3_BYTES, 1>(tmP[0], tmP[1], L.tmB, a, grid, s);
+  CUtensorMap tmBg;     // weights grouped: TPS k-blocks (taps) per box
+  if (L.stem) {
+    int rc = make_weight_tmap(L, 4, &tmBg); if (rc) return rc;
+    return launch_patch<64, false, 2, 2, STEM_PATCH_BYTES, 1, 4>(tmP[0], tmP[1], tmBg, a, grid, s);
+  }
+  if (L.bn == 64 && a.n_cblk == 1) {
+    int rc = make_weight_tmap(L, 9, &tmBg); if (rc) return rc;
+    return launch_patch<64, true, 3, 1, PATCH3_BYTES, 9, 1>(tmP[0], tmP[1], tmBg, a, grid, s);
+  }
+  if (L.bn == 128) {
+    int rc = make_weight_tmap(L, 3, &tmBg); if (rc) return rc;
+    return launch_patch<128, false, 3, 2, PATCH3_BYTES, 1, 3>(tmP[0], tmP[1], tmBg, a, grid, s);
+  }
   return PATCH_NOT_COVERED;
 }
 

@@ -111,24 +111,24 @@ blend_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
 
   if (warp == 0) {
     // ===================================================== TMA producer
-    if (lane == 0) {
+    {
       int stage = 0; uint32_t phase = 0, a_phase = 0;
       for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
         const int mt = u / args.n_chunks, chunk = u - mt * args.n_chunks;
         const int nt0 = chunk * args.n_chunk, nt1 = min(nt0 + args.n_chunk, args.n_tiles);
         mbar_wait(a_empty, a_phase ^ 1, 5);
-        mbar_arrive_expect_tx(a_full, L::A_TILES * TILE_BYTES);
+        if (elect_one()) mbar_arrive_expect_tx(a_full, L::A_TILES * TILE_BYTES);
         for (int kb = 0; kb < KBLKS; ++kb) {
-          tma_load_2d(smem + L::A_OFFSET + kb * TILE_BYTES, &tmAhi, a_full, kb * 64, mt * BM);
-          if (PASSES == 3) tma_load_2d(smem + L::A_OFFSET + (KBLKS + kb) * TILE_BYTES, &tmAlo, a_full, kb * 64, mt * BM);
+          if (elect_one()) tma_load_2d(smem + L::A_OFFSET + kb * TILE_BYTES, &tmAhi, a_full, kb * 64, mt * BM);
+          if (PASSES == 3) if (elect_one()) tma_load_2d(smem + L::A_OFFSET + (KBLKS + kb) * TILE_BYTES, &tmAlo, a_full, kb * 64, mt * BM);
         }
         a_phase ^= 1;
         for (int nt = nt0; nt < nt1; ++nt)
           for (int kb = 0; kb < KBLKS; ++kb)
             for (int part = 0; part < (PASSES == 3 ? 2 : 1); ++part) {
               mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-              mbar_arrive_expect_tx(&full_bar[stage], TILE_BYTES);
-              tma_load_2d(smem + L::B_OFFSET + stage * TILE_BYTES, part == 0 ? &tmBhi : &tmBlo, &full_bar[stage], kb * 64, nt * BN);
+              if (elect_one()) mbar_arrive_expect_tx(&full_bar[stage], TILE_BYTES);
+              if (elect_one()) tma_load_2d(smem + L::B_OFFSET + stage * TILE_BYTES, part == 0 ? &tmBhi : &tmBlo, &full_bar[stage], kb * 64, nt * BN);
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
       }
@@ -136,7 +136,7 @@ blend_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc_f16(BN);
       int stage = 0; uint32_t phase = 0, a_phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -159,26 +159,26 @@ blend_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
             mbar_wait(&full_bar[stage], phase, 3);
             tc_fence_after_sync();
             uint64_t bd = umma_desc_sw128(b_base + stage * TILE_BYTES);
-            for (int k = 0; k < nmma; ++k) umma_f16(d_tmem, ahi + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < nmma; ++k) if (elect_one()) umma_f16(d_tmem, ahi + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
             if (PASSES == 3) {
               const uint64_t alo = umma_desc_sw128(a_base + (KBLKS + kb) * TILE_BYTES);
-              for (int k = 0; k < nmma; ++k) umma_f16(d_tmem, alo + 2 * k, bd + 2 * k, idesc, 1u);
+              for (int k = 0; k < nmma; ++k) if (elect_one()) umma_f16(d_tmem, alo + 2 * k, bd + 2 * k, idesc, 1u);
             }
-            umma_commit(&empty_bar[stage]);
+            if (elect_one()) umma_commit(&empty_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             if (PASSES == 3) {   // B_lo[kb]:  A_hi B_lo
               mbar_wait(&full_bar[stage], phase, 3);
               tc_fence_after_sync();
               bd = umma_desc_sw128(b_base + stage * TILE_BYTES);
-              for (int k = 0; k < nmma; ++k) umma_f16(d_tmem, ahi + 2 * k, bd + 2 * k, idesc, 1u);
-              umma_commit(&empty_bar[stage]);
+              for (int k = 0; k < nmma; ++k) if (elect_one()) umma_f16(d_tmem, ahi + 2 * k, bd + 2 * k, idesc, 1u);
+              if (elect_one()) umma_commit(&empty_bar[stage]);
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
           }
-          umma_commit(&tmem_full[acc]);
+          if (elect_one()) umma_commit(&tmem_full[acc]);
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        umma_commit(a_empty);     // resident A tile may be overwritten once every MMA of this unit retired
+        if (elect_one()) umma_commit(a_empty);     // resident A tile may be overwritten once every MMA of this unit retired
       }
     }
     __syncwarp();
