@@ -173,9 +173,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const uint32_t a_addr = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint64_t a_desc = umma_desc_sw128(a_addr);
           const uint64_t b_desc = umma_desc_sw128(a_addr + A_BYTES);
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k)
-            if (elect_one()) umma_f16(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          if (elect_one()) umma_f16_x4(d_tmem, a_desc, b_desc, idesc, kb != 0 ? 1u : 0u);
           if (elect_one()) umma_commit(&empty_bar[stage]);                       // frees the smem slot when these MMAs retire
           if (kb == args.num_kb - 1) if (elect_one()) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -349,12 +347,10 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
             }
             const int p = args.t_patch[t];
             const uint32_t a_view = stage + (uint32_t)args.p_base[p] + (uint32_t)args.t_off[t] * 128u;
-            const uint64_t a_desc = umma_desc_sw128_sbo(a_view, 16u * 128u);     // 8-row groups are 16 pixels apart
+            const uint64_t a_desc = umma_desc_sw128_sbo(a_view, (uint32_t)args.p_pw[p] * 128u);   // 8-row groups are one patch row apart
             const uint64_t b_desc = umma_desc_sw128(b_addr);
             if (!(args.debug & 2)) {
-#pragma unroll
-              for (int j = 0; j < BLOCK_K / 16; ++j)
-                if (elect_one()) umma_f16(d_tmem, a_desc + (uint64_t)(2 * j), b_desc + (uint64_t)(2 * j), idesc, (cb | t | j) != 0 ? 1u : 0u);
+              if (elect_one()) umma_f16_x4(d_tmem, a_desc, b_desc, idesc, (cb | t) != 0 ? 1u : 0u);
             }
             if (!RESIDENT && (t % TPS) == TPS - 1) { if (elect_one()) umma_commit(&bempty[bs]); if (++bs == BS) { bs = 0; bphase ^= 1; } }
           }
@@ -635,7 +631,9 @@ int launch_patch(const CUtensorMap& p0, const CUtensorMap& p1, const CUtensorMap
 
 constexpr int PATCH_PW = 16;                                          // patch pitch in pixels (8 outputs + halo, padded)
 constexpr int PATCH3_BYTES = 18 * PATCH_PW * 128;                     // 3x3/1 halo patch of an 8x16 tile, 64 channels: 36 KB
-constexpr int STEM_PATCH_BYTES = (18 + 19) * PATCH_PW * 128;          // two row-parity patches of pixel pairs: 74 KB
+constexpr int STEM_PW = 12;                                           // stem patch pitch: 8 outputs + 3 halo pairs, padded to 12
+constexpr int STEM_PATCH_TX = (18 + 19) * STEM_PW * 128;              // two row-parity patches of pixel pairs: 55.5 KB
+constexpr int STEM_PATCH_BYTES = (STEM_PATCH_TX + 1023) / 1024 * 1024;  // ring stage pitch (1024-byte aligned)
 
 int run_patch_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N, int H, int W, const __half* residual,
                    int relu, __half* out, cudaStream_t s) {
@@ -665,22 +663,22 @@ int run_patch_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N,
     if (rc) return rc;
     tmP[1] = tmP[0];
   } else {   // stem: pixel pairs, two row-parity patches; tap index == weight k-block index = kh*4 + (dp+2)
-    a.n_cblk = 1; a.n_taps = 28; a.n_patch = 2; a.patch_tx = STEM_PATCH_BYTES;
+    a.n_cblk = 1; a.n_taps = 28; a.n_patch = 2; a.patch_tx = STEM_PATCH_TX;
     // parity 0 rows: kh = 1,3,5 -> dy = -1,0,1 (18 rows); parity 1 rows: kh = 0,2,4,6 -> dy = -2..1 (19 rows)
-    a.p_pw[0] = PATCH_PW; a.p_ph[0] = 18; a.p_ox[0] = -2; a.p_oy[0] = -1; a.p_base[0] = 0;
-    a.p_pw[1] = PATCH_PW; a.p_ph[1] = 19; a.p_ox[1] = -2; a.p_oy[1] = -2; a.p_base[1] = 18 * PATCH_PW * 128;
+    a.p_pw[0] = STEM_PW; a.p_ph[0] = 18; a.p_ox[0] = -2; a.p_oy[0] = -1; a.p_base[0] = 0;
+    a.p_pw[1] = STEM_PW; a.p_ph[1] = 19; a.p_ox[1] = -2; a.p_oy[1] = -2; a.p_base[1] = 18 * STEM_PW * 128;
     for (int kh = 0; kh < 7; ++kh) {
       const int o = kh - 3, ph = ((o % 2) + 2) % 2, dy = (o - ph) / 2;
       for (int dp = -2; dp <= 1; ++dp) {
         const int t = kh * 4 + (dp + 2);
         a.t_patch[t] = (uint8_t)ph;
-        a.t_off[t] = (uint16_t)((dy - a.p_oy[ph]) * PATCH_PW + (dp + 2));
+        a.t_off[t] = (uint16_t)((dy - a.p_oy[ph]) * STEM_PW + (dp + 2));
       }
     }
     for (int ph = 0; ph < 2; ++ph) {
       const uint64_t dims[4] = {64, (uint64_t)W / 2, (uint64_t)H / 2, Np};
       const uint64_t st[3] = {128, (uint64_t)2 * W * 64, (uint64_t)H * W * 64};
-      const uint32_t box[4] = {64, PATCH_PW, (uint32_t)a.p_ph[ph], 1};
+      const uint32_t box[4] = {64, STEM_PW, (uint32_t)a.p_ph[ph], 1};
       int rc = make_tmap_f16(&tmP[ph], in + (size_t)ph * W * 32, 4, dims, st, box, true);
       if (rc) return rc;
     }
@@ -689,7 +687,7 @@ int run_patch_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N,
   CUtensorMap tmBg;     // weights grouped: TPS k-blocks (taps) per box
   if (L.stem) {
     int rc = make_weight_tmap(L, 4, &tmBg); if (rc) return rc;
-    return launch_patch<64, false, 2, 2, STEM_PATCH_BYTES, 1, 4>(tmP[0], tmP[1], tmBg, a, grid, s);
+    return launch_patch<64, false, 2, 3, STEM_PATCH_BYTES, 1, 4>(tmP[0], tmP[1], tmBg, a, grid, s);
   }
   if (L.bn == 64 && a.n_cblk == 1) {
     int rc = make_weight_tmap(L, 9, &tmBg); if (rc) return rc;
