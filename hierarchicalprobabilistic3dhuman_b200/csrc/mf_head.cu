@@ -42,36 +42,53 @@ struct HeadTree {
   int anc_off[NBJ];
   int8_t n_anc[NBJ];
   int8_t anc[NBJ][MAX_ANC];
+  int8_t level_start[MAX_ANC + 2];   // joints grouped by tree depth (= number of ancestors): level l owns
+  int8_t level_joint[NBJ];           // level_joint[level_start[l] .. level_start[l+1])
+  int n_levels;
 };
+constexpr int HEAD_GROUPS = 5;       // joints of one depth processed concurrently (SMPL: at most 5 per level)
 
 namespace {
 
-// y[b][o] = act(sum_i x[b][i] Wt[i][o] + bias[o]); 8 batch rows x 32 outputs per CTA.
+// y[b][o] = act(sum_i x[b][i] Wt[i][o] + bias[o]): 16 batch rows x 64 outputs per CTA, K staged in 32-wide chunks
+// through shared memory (both operands), thread = 4 rows x 1 column.
 template <int ACT>  // 0 none, 1 ELU
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, int ldx, int K,
                                                      const float* __restrict__ Wt, const float* __restrict__ bias,
                                                      int O, float* __restrict__ y, int ldy, int B) {
-  extern __shared__ float sx[];   // [8][K]
-  const int b0 = blockIdx.y * 8, o = blockIdx.x * 32 + (threadIdx.x & 31), r = threadIdx.x >> 5;
-  for (int t = threadIdx.x; t < 8 * K; t += 256) {
-    const int rr = t / K, kk = t - rr * K;
-    sx[t] = (b0 + rr < B) ? x[(size_t)(b0 + rr) * ldx + kk] : 0.f;
+  __shared__ float sx[16][33];
+  __shared__ float sw[32][64];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;       // column, row group (4 rows each)
+  const int b0 = blockIdx.y * 16, o0 = blockIdx.x * 64;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    for (int i = threadIdx.x; i < 16 * 32; i += 256) {
+      const int r = i >> 5, kk = i & 31;
+      sx[r][kk] = (b0 + r < B && k0 + kk < K) ? x[(size_t)(b0 + r) * ldx + k0 + kk] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 32 * 64; i += 256) {
+      const int kk = i >> 6, c = i & 63;
+      sw[kk][c] = (k0 + kk < K && o0 + c < O) ? Wt[(size_t)(k0 + kk) * O + o0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 32; ++kk) {
+      const float w = sw[kk][tx];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = fmaf(sx[ty * 4 + r][kk], w, acc[r]);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  if (o >= O || b0 + r >= B) return;
-  const float* xr = sx + r * K;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int k = 0;
-  for (; k + 4 <= K; k += 4) {
-    a0 = fmaf(xr[k], Wt[(size_t)k * O + o], a0);
-    a1 = fmaf(xr[k + 1], Wt[(size_t)(k + 1) * O + o], a1);
-    a2 = fmaf(xr[k + 2], Wt[(size_t)(k + 2) * O + o], a2);
-    a3 = fmaf(xr[k + 3], Wt[(size_t)(k + 3) * O + o], a3);
+  if (o0 + tx >= O) return;
+  const float bz = bias[o0 + tx];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int bb = b0 + ty * 4 + r;
+    if (bb >= B) continue;
+    float v = acc[r] + bz;
+    if (ACT == 1) v = v > 0.f ? v : expm1f(v);
+    y[(size_t)bb * ldy + o0 + tx] = v;
   }
-  for (; k < K; ++k) a0 = fmaf(xr[k], Wt[(size_t)k * O + o], a0);
-  float v = (a0 + a1) + (a2 + a3) + bias[o];
-  if (ACT == 1) v = v > 0.f ? v : expm1f(v);
-  y[(size_t)(b0 + r) * ldy + o] = v;
 }
 
 // cat[b] = [feats_b | shape | glob | cam]; also writes the user-facing shape/glob/cam tensors.
@@ -94,7 +111,10 @@ __global__ void __launch_bounds__(256) pack_cat_kernel(const float* __restrict__
   }
 }
 
-__global__ void __launch_bounds__(HID) head_tree_kernel(const float* __restrict__ pre, const float* __restrict__ anc_wt,
+// One CTA per image, HEAD_GROUPS groups of 128 threads: joints of equal depth are independent given their
+// ancestors, so the 23 sequential steps of the reference collapse to 8 tree levels; each group runs one joint's
+// MLP (thread = hidden unit) and its leader runs the in-register SVD.
+__global__ void __launch_bounds__(HID * HEAD_GROUPS) head_tree_kernel(const float* __restrict__ pre, const float* __restrict__ anc_wt,
                                                         const float* __restrict__ w2, const float* __restrict__ b2,
                                                         HeadTree tree, float delta_i, int B,
                                                         const float* __restrict__ tUp, const float* __restrict__ tSp,
@@ -102,78 +122,94 @@ __global__ void __launch_bounds__(HID) head_tree_kernel(const float* __restrict_
                                                         float* __restrict__ U, float* __restrict__ S,
                                                         float* __restrict__ V, float* __restrict__ mode) {
   __shared__ float sUp[NBJ][9], sSp[NBJ][3], sMode[NBJ][9];
-  __shared__ float sIn[21 * MAX_ANC];
-  __shared__ float sPart[HID / 32][9];
-  __shared__ float sF[9];
-  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  __shared__ float sIn[HEAD_GROUPS][21 * MAX_ANC];
+  __shared__ float sPart[HEAD_GROUPS][HID / 32][9];
+  __shared__ float sF[HEAD_GROUPS][9];
+  const int b = blockIdx.x, grp = threadIdx.x / HID, t = threadIdx.x % HID, lane = t & 31, warp = t >> 5;
   if (tUp) {   // teacher forcing: ancestors' inputs come from the given tensors
-    for (int i = t; i < NBJ * 9; i += HID) { sUp[i / 9][i % 9] = tUp[(size_t)b * NBJ * 9 + i]; sMode[i / 9][i % 9] = tMode[(size_t)b * NBJ * 9 + i]; }
-    for (int i = t; i < NBJ * 3; i += HID) sSp[i / 3][i % 3] = tSp[(size_t)b * NBJ * 3 + i];
+    for (int i = threadIdx.x; i < NBJ * 9; i += blockDim.x) { sUp[i / 9][i % 9] = tUp[(size_t)b * NBJ * 9 + i]; sMode[i / 9][i % 9] = tMode[(size_t)b * NBJ * 9 + i]; }
+    for (int i = threadIdx.x; i < NBJ * 3; i += blockDim.x) sSp[i / 3][i % 3] = tSp[(size_t)b * NBJ * 3 + i];
   }
   __syncthreads();
-  for (int j = 0; j < NBJ; ++j) {
-    const int p = tree.n_anc[j];
-    // reference input layout (:126-130): [embed | U_p(anc 0..p-1) | S_p(anc ..) | mode(anc ..)]
-    for (int i = t; i < 21 * p; i += HID) {
-      float v;
-      if (i < 9 * p) v = sUp[tree.anc[j][i / 9]][i % 9];
-      else if (i < 12 * p) { const int q = i - 9 * p; v = sSp[tree.anc[j][q / 3]][q % 3]; }
-      else { const int q = i - 12 * p; v = sMode[tree.anc[j][q / 9]][q % 9]; }
-      sIn[i] = v;
-    }
-    __syncthreads();
-    float h = pre[(size_t)b * PRE + j * HID + t];
-    const float* wa = anc_wt + tree.anc_off[j];
-    for (int i = 0; i < 21 * p; ++i) h = fmaf(sIn[i], wa[i * HID + t], h);
-    h = h > 0.f ? h : expm1f(h);
-    // F = W2 h + b2 (+ delta I): per-warp partial dot products, then 9 threads finish
-    const float* w2j = w2 + (size_t)j * 9 * HID;
-#pragma unroll
-    for (int e = 0; e < 9; ++e) {
-      float v = w2j[e * HID + t] * h;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) sPart[warp][e] = v;
-    }
-    __syncthreads();
-    if (t < 9) {
-      float v = b2[j * 9 + t];
-#pragma unroll
-      for (int w = 0; w < HID / 32; ++w) v += sPart[w][t];
-      if (t == 0 || t == 4 || t == 8) v += delta_i;
-      sF[t] = v;
-    }
-    __syncthreads();
-    if (t == 0) {
-      float Fm[9], Um[9], Sm[3], Vm[9];
-#pragma unroll
-      for (int e = 0; e < 9; ++e) Fm[e] = sF[e];
-      svd3_lapack(Fm, Um, Sm, Vm);
-      const float du = det3(Um), dv = det3(Vm);
-      const size_t o9 = ((size_t)b * NBJ + j) * 9, o3 = ((size_t)b * NBJ + j) * 3;
-#pragma unroll
-      for (int e = 0; e < 9; ++e) { F[o9 + e] = Fm[e]; U[o9 + e] = Um[e]; V[o9 + e] = Vm[e]; }
-      S[o3] = Sm[0]; S[o3 + 1] = Sm[1]; S[o3 + 2] = Sm[2];
-      float Up[9], Vp[9];
-#pragma unroll
-      for (int e = 0; e < 9; ++e) { Up[e] = Um[e]; Vp[e] = Vm[e]; }
-      Up[2] *= du; Up[5] *= du; Up[8] *= du;
-      Vp[2] *= dv; Vp[5] *= dv; Vp[8] *= dv;
-      float Md[9];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          Md[r * 3 + c] = Up[r * 3] * Vp[c * 3] + Up[r * 3 + 1] * Vp[c * 3 + 1] + Up[r * 3 + 2] * Vp[c * 3 + 2];
-#pragma unroll
-      for (int e = 0; e < 9; ++e) mode[o9 + e] = Md[e];
-      if (!tUp) {
-#pragma unroll
-        for (int e = 0; e < 9; ++e) { sUp[j][e] = Up[e]; sMode[j][e] = Md[e]; }
-        sSp[j][0] = Sm[0]; sSp[j][1] = Sm[1]; sSp[j][2] = Sm[2] * (du * dv);
+  for (int l = 0; l < tree.n_levels; ++l) {
+    for (int base = tree.level_start[l]; base < tree.level_start[l + 1]; base += HEAD_GROUPS) {
+      const bool active = base + grp < tree.level_start[l + 1];
+      const int j = active ? tree.level_joint[base + grp] : 0;
+      const int p = tree.n_anc[j];
+      if (active) {   // reference input layout (:126-130): [embed | U_p(anc 0..p-1) | S_p(anc ..) | mode(anc ..)]
+        for (int i = t; i < 21 * p; i += HID) {
+          float v;
+          if (i < 9 * p) v = sUp[tree.anc[j][i / 9]][i % 9];
+          else if (i < 12 * p) { const int q = i - 9 * p; v = sSp[tree.anc[j][q / 3]][q % 3]; }
+          else { const int q = i - 12 * p; v = sMode[tree.anc[j][q / 9]][q % 9]; }
+          sIn[grp][i] = v;
+        }
       }
+      __syncthreads();
+      if (active) {
+        float h = pre[(size_t)b * PRE + j * HID + t];
+        const float* wa = anc_wt + tree.anc_off[j];
+        float h1 = 0.f, h2 = 0.f, h3 = 0.f;
+        int i = 0;
+        for (; i + 4 <= 21 * p; i += 4) {
+          h = fmaf(sIn[grp][i], wa[i * HID + t], h);
+          h1 = fmaf(sIn[grp][i + 1], wa[(i + 1) * HID + t], h1);
+          h2 = fmaf(sIn[grp][i + 2], wa[(i + 2) * HID + t], h2);
+          h3 = fmaf(sIn[grp][i + 3], wa[(i + 3) * HID + t], h3);
+        }
+        for (; i < 21 * p; ++i) h = fmaf(sIn[grp][i], wa[i * HID + t], h);
+        h = (h + h1) + (h2 + h3);
+        h = h > 0.f ? h : expm1f(h);
+        // F = W2 h + b2 (+ delta I): per-warp partial dot products, then 9 threads finish
+        const float* w2j = w2 + (size_t)j * 9 * HID;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) {
+          float v = w2j[e * HID + t] * h;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0) sPart[grp][warp][e] = v;
+        }
+      }
+      __syncthreads();
+      if (active && t < 9) {
+        float v = b2[j * 9 + t];
+#pragma unroll
+        for (int w = 0; w < HID / 32; ++w) v += sPart[grp][w][t];
+        if (t == 0 || t == 4 || t == 8) v += delta_i;
+        sF[grp][t] = v;
+      }
+      __syncthreads();
+      if (active && t == 0) {
+        float Fm[9], Um[9], Sm[3], Vm[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Fm[e] = sF[grp][e];
+        svd3_lapack(Fm, Um, Sm, Vm);
+        const float du = det3(Um), dv = det3(Vm);
+        const size_t o9 = ((size_t)b * NBJ + j) * 9, o3 = ((size_t)b * NBJ + j) * 3;
+#pragma unroll
+        for (int e = 0; e < 9; ++e) { F[o9 + e] = Fm[e]; U[o9 + e] = Um[e]; V[o9 + e] = Vm[e]; }
+        S[o3] = Sm[0]; S[o3 + 1] = Sm[1]; S[o3 + 2] = Sm[2];
+        float Up[9], Vp[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) { Up[e] = Um[e]; Vp[e] = Vm[e]; }
+        Up[2] *= du; Up[5] *= du; Up[8] *= du;
+        Vp[2] *= dv; Vp[5] *= dv; Vp[8] *= dv;
+        float Md[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            Md[r * 3 + c] = Up[r * 3] * Vp[c * 3] + Up[r * 3 + 1] * Vp[c * 3 + 1] + Up[r * 3 + 2] * Vp[c * 3 + 2];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) mode[o9 + e] = Md[e];
+        if (!tUp) {
+#pragma unroll
+          for (int e = 0; e < 9; ++e) { sUp[j][e] = Up[e]; sMode[j][e] = Md[e]; }
+          sSp[j][0] = Sm[0]; sSp[j][1] = Sm[1]; sSp[j][2] = Sm[2] * (du * dv);
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -296,18 +332,29 @@ extern "C" int hp3d_head_forward(const hp3d_head* h, const float* feats, int B, 
   float* cat = small + (size_t)B * 32;
   float* embed = cat + (size_t)B * CATP;
   float* pre = embed + (size_t)B * EMBED;
-  const int gy = cdiv(B, 8);
-  linear_kernel<1><<<dim3(cdiv(FC1, 32), gy), 256, 8 * FEAT * sizeof(float), stream>>>(feats, FEAT, FEAT, h->fc1_wt, h->fc1_b, FC1, x, FC1, B);
-  linear_kernel<0><<<dim3(1, gy), 256, 8 * FC1 * sizeof(float), stream>>>(x, FC1, FC1, h->small_wt, h->small_b, 32, small, 32, B);
+  const int gy = cdiv(B, 16);
+  linear_kernel<1><<<dim3(cdiv(FC1, 64), gy), 256, 0, stream>>>(feats, FEAT, FEAT, h->fc1_wt, h->fc1_b, FC1, x, FC1, B);
+  linear_kernel<0><<<dim3(1, gy), 256, 0, stream>>>(x, FC1, FC1, h->small_wt, h->small_b, 32, small, 32, B);
   pack_cat_kernel<<<B, 256, 0, stream>>>(feats, small, B, cat, shape_params, glob, cam);
-  linear_kernel<1><<<dim3(cdiv(EMBED, 32), gy), 256, 8 * CAT * sizeof(float), stream>>>(cat, CATP, CAT, h->embed_wt, h->embed_b, EMBED, embed, EMBED, B);
-  linear_kernel<0><<<dim3(cdiv(PRE, 32), gy), 256, 8 * EMBED * sizeof(float), stream>>>(embed, EMBED, EMBED, h->pre_wt, h->pre_b, PRE, pre, PRE, B);
+  linear_kernel<1><<<dim3(cdiv(EMBED, 64), gy), 256, 0, stream>>>(cat, CATP, CAT, h->embed_wt, h->embed_b, EMBED, embed, EMBED, B);
+  linear_kernel<0><<<dim3(cdiv(PRE, 64), gy), 256, 0, stream>>>(embed, EMBED, EMBED, h->pre_wt, h->pre_b, PRE, pre, PRE, B);
   HeadTree tree;
   for (int j = 0; j < NBJ; ++j) {
     tree.anc_off[j] = h->anc_off[j];
     tree.n_anc[j] = (int8_t)h->n_anc[j];
     for (int a = 0; a < MAX_ANC; ++a) tree.anc[j][a] = (int8_t)(a < h->n_anc[j] ? h->anc[j][a] : 0);
   }
-  head_tree_kernel<<<B, HID, 0, stream>>>(pre, h->anc_wt, h->w2, h->b2, tree, h->delta_i, B, tUp, tSp, tMode, F, U, S, V, mode);
+  {   // group joints by depth (number of ancestors); within a level keep index order
+    int n = 0, lv = 0;
+    for (int d = 0; d <= MAX_ANC && n < NBJ; ++d) {
+      tree.level_start[lv] = (int8_t)n;
+      int cnt = 0;
+      for (int j = 0; j < NBJ; ++j) if (h->n_anc[j] == d) { tree.level_joint[n++] = (int8_t)j; ++cnt; }
+      if (cnt) ++lv;
+    }
+    tree.level_start[lv] = (int8_t)n;
+    tree.n_levels = lv;
+  }
+  head_tree_kernel<<<B, HID * HEAD_GROUPS, 0, stream>>>(pre, h->anc_wt, h->w2, h->b2, tree, h->delta_i, B, tUp, tSp, tMode, F, U, S, V, mode);
   return launch_status("head kernels");
 }

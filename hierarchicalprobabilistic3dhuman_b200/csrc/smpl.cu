@@ -556,6 +556,73 @@ __global__ void __launch_bounds__(256) vertex_uncertainty_kernel(const float* __
   }
 }
 
+// Single-read variant: a CTA stages ALL N samples of 64 consecutive vertices (N x 768 B, contiguous per sample)
+// in shared memory with one coalesced pass over HBM, then computes the mean and the mean distance from it out of
+// shared memory. Halves the HBM traffic of the two-pass kernel above (which remains the fallback for N > 280).
+constexpr int UNC_TV = 64;
+__global__ void __launch_bounds__(256) vertex_uncertainty_smem_kernel(const float* __restrict__ verts, int B, int N,
+                                                                      float* __restrict__ mean_out,
+                                                                      float* __restrict__ dist_out) {
+  extern __shared__ float us[];                       // [N][192] samples | [192] mean | [4][64] partial distances
+  const int b = blockIdx.y, v0 = blockIdx.x * UNC_TV;
+  const int nfl = min(UNC_TV, NV - v0) * 3;           // floats per sample in this tile (192, last tile 126)
+  const int t = threadIdx.x;
+  float* mean = us + (size_t)N * 192;
+  float* part = mean + 192;
+  const float* base = verts + (size_t)b * N * NV3 + (size_t)v0 * 3;
+  {   // warp w stages samples w, w+8, ...; four samples (24 independent 128-byte row loads per warp) in flight at a time
+    const int w = t >> 5, lane = t & 31;
+    for (int n0 = w; n0 < N; n0 += 32) {
+      float r[4][6];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int n = n0 + 8 * u;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const int f = lane + 32 * i;
+          r[u][i] = (n < N && f < nfl) ? base[(size_t)n * NV3 + f] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int n = n0 + 8 * u;
+        if (n < N) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) us[n * 192 + lane + 32 * i] = r[u][i];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (t < 192) {
+    float s0 = 0.f, s1 = 0.f;
+    int n = 0;
+    for (; n + 1 < N; n += 2) { s0 += us[n * 192 + t]; s1 += us[(n + 1) * 192 + t]; }
+    if (n < N) s0 += us[n * 192 + t];
+    mean[t] = (s0 + s1) / (float)N;
+  }
+  __syncthreads();
+  {
+    const int v = t & 63, q = t >> 6;
+    const float mx = mean[3 * v], my = mean[3 * v + 1], mz = mean[3 * v + 2];
+    float acc = 0.f;
+    for (int n = q; n < N; n += 4) {
+      const float* p = us + n * 192 + 3 * v;
+      const float dx = p[0] - mx, dy = p[1] - my, dz = p[2] - mz;
+      acc += sqrtf(dx * dx + dy * dy + dz * dz);
+    }
+    part[q * 64 + v] = acc;
+  }
+  __syncthreads();
+  if (t < 64 && v0 + t < NV) {
+    dist_out[(size_t)b * NV + v0 + t] = (part[t] + part[64 + t] + part[128 + t] + part[192 + t]) / (float)N;
+    if (mean_out) {
+      float* mo = mean_out + ((size_t)b * NV + v0 + t) * 3;
+      mo[0] = mean[3 * t]; mo[1] = mean[3 * t + 1]; mo[2] = mean[3 * t + 2];
+    }
+  }
+}
+
 // ------------------------------------------------------------------ host side
 namespace hp3d {
 int blend_tc_create(const double* posedirs, const double* shapedirs, const double* v_template, void** out);   // gemm_tc.cu
@@ -812,6 +879,14 @@ extern "C" int hp3d_rot6d_to_rotmat(const float* x, int n, float* R, void* strea
 extern "C" int hp3d_vertex_uncertainty(const float* vertices, int B, int N, float* mean_vertices, float* avg_dist,
                                        void* stream) {
   HP3D_ARG(vertices && avg_dist && B > 0 && N > 0, "bad argument");
+  const size_t smem = ((size_t)N * 192 + 192 + 256) * sizeof(float);
+  if (smem <= 220 * 1024) {
+    static size_t attr = 0;
+    if (smem > attr) { HP3D_CUDA(cudaFuncSetAttribute(vertex_uncertainty_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    dim3 grid(cdiv(NV, UNC_TV), B);
+    vertex_uncertainty_smem_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(vertices, B, N, mean_vertices, avg_dist);
+    return launch_status("vertex_uncertainty_smem_kernel");
+  }
   dim3 grid(cdiv(NV, 256), B);
   vertex_uncertainty_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(vertices, B, N, mean_vertices, avg_dist);
   return launch_status("vertex_uncertainty_kernel");
