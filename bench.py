@@ -213,16 +213,35 @@ def main_hp3d(args):
     # gather buffers: every rank's kernels write straight into its slice (no pack/copy)
     from hierarchicalprobabilistic3dhuman_b200.distributed import GatherBuffers
     full = args.gather == "full"
-    specs = {"rotmats": (N, 23, 3, 3), "betas": (10,), "uncertainty": (6890,)}
-    if full:
-        specs["vertices"] = (N, 6890, 3)
-    gb = GatherBuffers(B, specs, dev, rank=rank, world=world)
-    verts_local = gb.local("vertices") if full else torch.empty(B, N, 6890, 3, device=dev)
+    gb = GatherBuffers(B, {"rotmats": (N, 23, 3, 3), "betas": (10,), "uncertainty": (6890,)}, dev, rank=rank, world=world)
+    # sample vertices (BASELINE configs[3]): gathered per image chunk so the NVLink transfer of chunk c overlaps the
+    # SMPL kernels of chunk c+1; layout (chunk, rank, image-in-chunk, N, 6890, 3)
+    VC = 4 if (full and world > 1 and B % 4 == 0) else 1
+    cbv = B // VC
+    g_verts = torch.empty(VC, world if full else 1, cbv, N, 6890, 3, device=dev)
+    my = rank if full else 0
+    comm_stream = torch.cuda.Stream(device=dev)
+    chunk_events = []
+
+    def on_chunk(c):
+        if world > 1 and full:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(ev)
+                dist.all_gather_into_tensor(g_verts[c].view(world * cbv, N, 6890, 3), g_verts[c, my])
+
     pipe = hp.HotPathPipeline(net, smpl, B, N, dev, rotmats_out=gb.local("rotmats"), betas_out=gb.local("betas"),
-                              vertices_out=verts_local, uncertainty_out=gb.local("uncertainty"))
+                              vertices_out=[g_verts[c, my] for c in range(VC)], uncertainty_out=gb.local("uncertainty"),
+                              on_vertices_chunk=on_chunk)
     L = _lib.lib()
     h_smpl, joints = pipe.h_smpl, pipe.joints
-    gather = gb.all_gather
+    verts_local = g_verts[0, my]
+
+    def gather():
+        gb.all_gather()
+        if world > 1 and full:
+            torch.cuda.current_stream().wait_stream(comm_stream)
 
     def step(x):
         pipe.run_device(x)
@@ -274,19 +293,19 @@ def main_hp3d(args):
     d2h_bytes = pipe.d2h_bytes()
 
     # ---- dominant memory-bound kernel alone: SMPL-LBS (FK + skinning + joints)
-    M = B * N
+    M = cbv * N
     vp = torch.empty(M, 20670, device=dev).normal_()
-    Jt = torch.randn(B, 24, 3, device=dev)
-    gR = hp.rot6d_to_rotmat(torch.randn(B, 6, device=dev))
-    Rr = gb.local("rotmats").contiguous()
+    Jt = torch.randn(cbv, 24, 3, device=dev)
+    gR = hp.rot6d_to_rotmat(torch.randn(cbv, 6, device=dev))
+    Rr = gb.local("rotmats")[:cbv].contiguous()
     for _ in range(3):
-        _lib.check(L.hp3d_smpl_lbs(h_smpl, vp.data_ptr(), Jt.data_ptr(), B, gR.data_ptr(), B, Rr.data_ptr(), M,
+        _lib.check(L.hp3d_smpl_lbs(h_smpl, vp.data_ptr(), Jt.data_ptr(), cbv, gR.data_ptr(), cbv, Rr.data_ptr(), M,
                                    verts_local.data_ptr(), joints.data_ptr(), _lib.stream_ptr()))
     torch.cuda.synchronize()
     reps = 5
     e0.record()
     for _ in range(reps):
-        _lib.check(L.hp3d_smpl_lbs(h_smpl, vp.data_ptr(), Jt.data_ptr(), B, gR.data_ptr(), B, Rr.data_ptr(), M,
+        _lib.check(L.hp3d_smpl_lbs(h_smpl, vp.data_ptr(), Jt.data_ptr(), cbv, gR.data_ptr(), cbv, Rr.data_ptr(), M,
                                    verts_local.data_ptr(), joints.data_ptr(), _lib.stream_ptr()))
     e1.record()
     torch.cuda.synchronize()
@@ -319,7 +338,8 @@ def main_hp3d(args):
                 "clocks": clocks,
                 "roofline": {"kernel": "lbs_kernel (SMPL FK + skinning + 90 joints)", "bound": "hbm", "achieved": achieved,
                              "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                             "traffic": None, "ms": lbs_ms, "meshes": M, "bytes_per_mesh": LBS_BYTES_PER_MESH}}
+                             "traffic": 4.2932e9 if M == 25600 else None, "traffic_source": "profiles/r01d_ncu_full_summary.csv (dram read 2.1476 GB + write 2.1456 GB per launch at 25,600 meshes)",
+                             "ms": lbs_ms, "meshes": M, "bytes_per_mesh": LBS_BYTES_PER_MESH}}
         if not args.no_cpu_baseline and world == 1:
             cb, _ = time_cpu_reference(2, 1, args.ref_batch, N)
             line["cpu_baseline"] = cb

@@ -559,63 +559,65 @@ __global__ void __launch_bounds__(256) vertex_uncertainty_kernel(const float* __
 // Single-read variant: a CTA stages ALL N samples of 64 consecutive vertices (N x 768 B, contiguous per sample)
 // in shared memory with one coalesced pass over HBM, then computes the mean and the mean distance from it out of
 // shared memory. Halves the HBM traffic of the two-pass kernel above (which remains the fallback for N > 280).
-constexpr int UNC_TV = 64;
+constexpr int UNC_TV = 32;                 // vertices per CTA: 96 floats (384 B) per sample, N x 384 B of shared memory
+constexpr int UNC_F = UNC_TV * 3;
 __global__ void __launch_bounds__(256) vertex_uncertainty_smem_kernel(const float* __restrict__ verts, int B, int N,
                                                                       float* __restrict__ mean_out,
                                                                       float* __restrict__ dist_out) {
-  extern __shared__ float us[];                       // [N][192] samples | [192] mean | [4][64] partial distances
+  extern __shared__ float us[];                       // [N][96] samples | [96] mean | [8][32] partial distances
   const int b = blockIdx.y, v0 = blockIdx.x * UNC_TV;
-  const int nfl = min(UNC_TV, NV - v0) * 3;           // floats per sample in this tile (192, last tile 126)
-  const int t = threadIdx.x;
-  float* mean = us + (size_t)N * 192;
-  float* part = mean + 192;
+  const int nfl = min(UNC_TV, NV - v0) * 3;           // floats per sample in this tile (96, last tile 30)
+  const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+  float* mean = us + (size_t)N * UNC_F;
+  float* part = mean + UNC_F;
   const float* base = verts + (size_t)b * N * NV3 + (size_t)v0 * 3;
-  {   // warp w stages samples w, w+8, ...; four samples (24 independent 128-byte row loads per warp) in flight at a time
-    const int w = t >> 5, lane = t & 31;
-    for (int n0 = w; n0 < N; n0 += 32) {
-      float r[4][6];
+  // warp w stages samples w, w+8, ...; eight samples (24 independent row loads per lane) in flight at a time
+  for (int n0 = w; n0 < N; n0 += 64) {
+    float r[8][3];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int n = n0 + 8 * u;
+    for (int u = 0; u < 8; ++u) {
+      const int n = n0 + 8 * u;
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const int f = lane + 32 * i;
-          r[u][i] = (n < N && f < nfl) ? base[(size_t)n * NV3 + f] : 0.f;
-        }
+      for (int i = 0; i < 3; ++i) {
+        const int f = lane + 32 * i;
+        r[u][i] = (n < N && f < nfl) ? base[(size_t)n * NV3 + f] : 0.f;
       }
+    }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int n = n0 + 8 * u;
-        if (n < N) {
+    for (int u = 0; u < 8; ++u) {
+      const int n = n0 + 8 * u;
+      if (n < N) {
 #pragma unroll
-          for (int i = 0; i < 6; ++i) us[n * 192 + lane + 32 * i] = r[u][i];
-        }
+        for (int i = 0; i < 3; ++i) us[n * UNC_F + lane + 32 * i] = r[u][i];
       }
     }
   }
   __syncthreads();
-  if (t < 192) {
+  if (t < UNC_F) {
     float s0 = 0.f, s1 = 0.f;
     int n = 0;
-    for (; n + 1 < N; n += 2) { s0 += us[n * 192 + t]; s1 += us[(n + 1) * 192 + t]; }
-    if (n < N) s0 += us[n * 192 + t];
+    for (; n + 1 < N; n += 2) { s0 += us[n * UNC_F + t]; s1 += us[(n + 1) * UNC_F + t]; }
+    if (n < N) s0 += us[n * UNC_F + t];
     mean[t] = (s0 + s1) / (float)N;
   }
   __syncthreads();
   {
-    const int v = t & 63, q = t >> 6;
+    const int v = lane, q = w;                        // 8 sample groups x 32 vertices
     const float mx = mean[3 * v], my = mean[3 * v + 1], mz = mean[3 * v + 2];
     float acc = 0.f;
-    for (int n = q; n < N; n += 4) {
-      const float* p = us + n * 192 + 3 * v;
+    for (int n = q; n < N; n += 8) {
+      const float* p = us + n * UNC_F + 3 * v;
       const float dx = p[0] - mx, dy = p[1] - my, dz = p[2] - mz;
       acc += sqrtf(dx * dx + dy * dy + dz * dz);
     }
-    part[q * 64 + v] = acc;
+    part[q * 32 + v] = acc;
   }
   __syncthreads();
-  if (t < 64 && v0 + t < NV) {
-    dist_out[(size_t)b * NV + v0 + t] = (part[t] + part[64 + t] + part[128 + t] + part[192 + t]) / (float)N;
+  if (t < 32 && v0 + t < NV) {
+    float a = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a += part[q * 32 + t];
+    dist_out[(size_t)b * NV + v0 + t] = a / (float)N;
     if (mean_out) {
       float* mo = mean_out + ((size_t)b * NV + v0 + t) * 3;
       mo[0] = mean[3 * t]; mo[1] = mean[3 * t + 1]; mo[2] = mean[3 * t + 2];
@@ -879,7 +881,7 @@ extern "C" int hp3d_rot6d_to_rotmat(const float* x, int n, float* R, void* strea
 extern "C" int hp3d_vertex_uncertainty(const float* vertices, int B, int N, float* mean_vertices, float* avg_dist,
                                        void* stream) {
   HP3D_ARG(vertices && avg_dist && B > 0 && N > 0, "bad argument");
-  const size_t smem = ((size_t)N * 192 + 192 + 256) * sizeof(float);
+  const size_t smem = ((size_t)N * UNC_F + UNC_F + 256) * sizeof(float);
   if (smem <= 220 * 1024) {
     static size_t attr = 0;
     if (smem > attr) { HP3D_CUDA(cudaFuncSetAttribute(vertex_uncertainty_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }

@@ -18,26 +18,37 @@ from .sampling import pose_matrix_fisher_sampling_torch
 
 class HotPathPipeline:
     def __init__(self, net, smpl, batch, num_samples, device, rotmats_out=None, betas_out=None, vertices_out=None,
-                 uncertainty_out=None, chunks=4):
+                 uncertainty_out=None, chunks=4, on_vertices_chunk=None):
+        """`vertices_out` may be one (B,N,6890,3) tensor or a list of equally sized chunk tensors (cb,N,6890,3) --
+        e.g. this rank's slices of per-chunk all-gather buffers; `on_vertices_chunk(c)` is then called right after
+        chunk c's SMPL kernels are enqueued, so a collective on another stream can overlap the next chunk."""
         self.net, self.smpl, self.B, self.N, self.dev = net, smpl, batch, num_samples, torch.device(device)
         B, N, dev = batch, num_samples, self.dev
         mk = lambda t, *s: t if t is not None else torch.empty(*s, device=dev, dtype=torch.float32)
         self.rotmats = mk(rotmats_out, B, N, 23, 3, 3)
         self.betas = mk(betas_out, B, 10)
-        self.vertices = mk(vertices_out, B, N, 6890, 3)
+        if isinstance(vertices_out, (list, tuple)):
+            self.vertex_chunks = list(vertices_out)
+            self.vertices = None
+            assert B % len(self.vertex_chunks) == 0
+        else:
+            self.vertices = mk(vertices_out, B, N, 6890, 3)
+            self.vertex_chunks = [self.vertices]
+        self.on_vertices_chunk = on_vertices_chunk
         self.uncertainty = mk(uncertainty_out, B, 6890)
-        for t in (self.rotmats, self.betas, self.vertices, self.uncertainty):
+        for t in [self.rotmats, self.betas, self.uncertainty] + self.vertex_chunks:
             assert t.is_contiguous() and t.device == dev
         self.joints = torch.empty(B * N, 90, 3, device=dev)
         self.L = _lib.lib()
         self.h_smpl = smpl._handle(dev)
-        self.ws = torch.empty(self.L.hp3d_smpl_workspace_bytes(self.h_smpl, B * N, B), dtype=torch.uint8, device=dev)
+        cb = B // len(self.vertex_chunks)
+        self.ws = torch.empty(self.L.hp3d_smpl_workspace_bytes(self.h_smpl, cb * N, cb), dtype=torch.uint8, device=dev)
         # host-streaming state
         self.chunks = chunks if B % chunks == 0 else 1
         self._stage = None
         self._slot = 0
         # kernels launched by one pass (ResNet-18 fast mode 23, head 6, rot6d 1, SMPL 4+4, sampler 1, stats 1, betas copy 1)
-        self.launches_per_pass = 23 + 6 + 1 + 4 + 1 + 4 + 1 + 1
+        self.launches_per_pass = 23 + 6 + 1 + 4 + 1 + (4 + 1) * len(self.vertex_chunks) + 1
 
     # ------------------------------------------------------------------ device-resident pass
     def _after_encoder(self, feats):
@@ -48,11 +59,17 @@ class HotPathPipeline:
         out_mode = self.smpl(body_pose=mode, global_orient=glob_R.unsqueeze(1), betas=loc, pose2rot=False)
         R = pose_matrix_fisher_sampling_torch(U, S, V, N, out=self.rotmats)
         self.betas.copy_(loc)
-        _lib.check(L.hp3d_smpl_forward(self.h_smpl, loc.data_ptr(), B, glob_R.data_ptr(), B, R.data_ptr(), B * N,
-                                       self.vertices.data_ptr(), self.joints.data_ptr(), self.ws.data_ptr(),
-                                       self.ws.numel(), _lib.stream_ptr()), "hp3d_smpl_forward")
-        _lib.check(L.hp3d_vertex_uncertainty(self.vertices.data_ptr(), B, N, None, self.uncertainty.data_ptr(),
-                                             _lib.stream_ptr()), "hp3d_vertex_uncertainty")
+        C = len(self.vertex_chunks)
+        cb = B // C
+        for c, vch in enumerate(self.vertex_chunks):       # images [c*cb, (c+1)*cb): SMPL on cb*N meshes + statistics
+            i0 = c * cb
+            _lib.check(L.hp3d_smpl_forward(self.h_smpl, loc[i0:].data_ptr(), cb, glob_R[i0:].data_ptr(), cb, R[i0:].data_ptr(),
+                                           cb * N, vch.data_ptr(), self.joints[i0 * N:].data_ptr(), self.ws.data_ptr(),
+                                           self.ws.numel(), _lib.stream_ptr()), "hp3d_smpl_forward")
+            _lib.check(L.hp3d_vertex_uncertainty(vch.data_ptr(), cb, N, None, self.uncertainty[i0:].data_ptr(),
+                                                 _lib.stream_ptr()), "hp3d_vertex_uncertainty")
+            if self.on_vertices_chunk is not None:
+                self.on_vertices_chunk(c)
         return dict(mode_vertices=out_mode.vertices, mode_joints=out_mode.joints, joints=self.joints, rotmats=R,
                     uncertainty=self.uncertainty, vertices=self.vertices, betas=self.betas, pose_S=S, cam=cam)
 
