@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="one warm-up + the timed steps only (for ncu): no e2e / LBS-alone / CPU legs")
     ap.add_argument("--ref-threads", type=int, default=0, help="torch CPU threads for the reference arm (0 = pick the best of a sweep)")
+    ap.add_argument("--transport", default="nccl", choices=["p2p", "nccl"],
+                    help="N>1 vertices gather: NCCL (default) or EXPERIMENTAL copy-engine peer pushes over CUDA IPC")
     ap.add_argument("--gather", default="full", choices=["full", "stats"],
                     help="N>1: all-gather (rotmats, betas, vertices) [configs[3]] or per-image statistics only")
     return ap.parse_args()
@@ -218,32 +220,64 @@ def main_hp3d(args):
     # SMPL kernels of chunk c+1; layout (chunk, rank, image-in-chunk, N, 6890, 3)
     VC = 4 if (full and world > 1 and B % 4 == 0) else 1
     cbv = B // VC
-    g_verts = torch.empty(VC, world if full else 1, cbv, N, 6890, 3, device=dev)
+    # two buffer sets: the NVLink gather of step i also overlaps the encoder of step i+1
+    NBUF = 2 if (full and world > 1) else 1
+    g_verts = [torch.empty(VC, world if full else 1, cbv, N, 6890, 3, device=dev) for _ in range(NBUF)]
     my = rank if full else 0
     comm_stream = torch.cuda.Stream(device=dev)
-    chunk_events = []
+    state = {"k": 0, "pending": [None] * NBUF, "count": 0}
+
+    # transport of the big vertices gather: peer-to-peer pushes on the copy engines (no SMs) if CUDA IPC works
+    from hierarchicalprobabilistic3dhuman_b200.distributed import PeerPush
+    pushers = None
+    if world > 1 and full and args.transport == "p2p":
+        pushers = [PeerPush(g, rank, world) for g in g_verts]
+        if not all(p_.ok for p_ in pushers):
+            pushers = None
+    transport = "p2p-copy-engine" if pushers else ("nccl" if (world > 1 and full) else "none")
 
     def on_chunk(c):
         if world > 1 and full:
+            gv = g_verts[state["k"]]
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
-            with torch.cuda.stream(comm_stream):
-                comm_stream.wait_event(ev)
-                dist.all_gather_into_tensor(g_verts[c].view(world * cbv, N, 6890, 3), g_verts[c, my])
+            comm_stream.wait_event(ev)
+            if pushers:
+                pushers[state["k"]].push(lambda buf, c=c: buf[c, my], comm_stream)
+            else:
+                with torch.cuda.stream(comm_stream):
+                    dist.all_gather_into_tensor(gv[c].view(world * cbv, N, 6890, 3), gv[c, my])
 
     pipe = hp.HotPathPipeline(net, smpl, B, N, dev, rotmats_out=gb.local("rotmats"), betas_out=gb.local("betas"),
-                              vertices_out=[g_verts[c, my] for c in range(VC)], uncertainty_out=gb.local("uncertainty"),
+                              vertices_out=[g_verts[0][c, my] for c in range(VC)], uncertainty_out=gb.local("uncertainty"),
                               on_vertices_chunk=on_chunk)
     L = _lib.lib()
     h_smpl, joints = pipe.h_smpl, pipe.joints
-    verts_local = g_verts[0, my]
+    verts_local = g_verts[0][0, my]
+
+    def begin_step():
+        k = state["count"] % NBUF
+        state["k"] = k
+        if state["pending"][k] is not None:                 # the gather that last used this buffer set must be done
+            torch.cuda.current_stream().wait_event(state["pending"][k])
+        pipe.vertex_chunks = [g_verts[k][c, my] for c in range(VC)]
 
     def gather():
         gb.all_gather()
         if world > 1 and full:
+            if pushers:
+                pushers[state["k"]].fence(comm_stream)       # all ranks' pushes of this step have landed
+            ev = torch.cuda.Event()
+            ev.record(comm_stream)
+            state["pending"][state["k"]] = ev
+        state["count"] += 1
+
+    def finish():
+        if world > 1 and full:
             torch.cuda.current_stream().wait_stream(comm_stream)
 
     def step(x):
+        begin_step()
         pipe.run_device(x)
         gather()
 
@@ -258,12 +292,14 @@ def main_hp3d(args):
     # ---- device-resident timing
     for _ in range(1 if args.profile else max(args.warmup, 3)):
         step(x_dev)
+    finish()
     sync_all()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         e0.record()
         for _ in range(args.steps):
             step(x_dev)
+        finish()
         e1.record()
         sync_all()
     ms = e0.elapsed_time(e1) / args.steps
@@ -278,14 +314,18 @@ def main_hp3d(args):
     x_hosts = [x_host, x_host.clone().pin_memory()]
     last = None
     for i in range(2):
+        begin_step()
         last = pipe.run_host(x_hosts[i & 1])
         gather()
+    finish()
     last[1].synchronize()
     sync_all()
     e0.record()
     for i in range(args.steps):
+        begin_step()
         last = pipe.run_host(x_hosts[i & 1])
         gather()
+    finish()
     last[1].synchronize()
     e1.record()
     sync_all()
@@ -326,7 +366,7 @@ def main_hp3d(args):
                 "data": "synthetic",
                 "config": {"workload": f"BASELINE configs[1]/[3] at the metric's batch: {B} images/GPU x N={N} samples, 18x256x256 proxy rep, "
                                        f"full hot path (encoder+head+sampler+SMPL on {B * N} meshes/GPU)",
-                           "encoder_mode": args.encoder_mode, "gather": args.gather if world > 1 else "none",
+                           "encoder_mode": args.encoder_mode, "gather": args.gather if world > 1 else "none", "gather_transport": transport,
                            "l2": "inputs (1.2 GB/step) and outputs (2.1 GB/step) exceed the 126 MB L2; no explicit flush",
                            "smpl": "synthetic SMPL-shaped model (licence-gated file absent)", "rng": "in-kernel Philox"},
                 "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s",
