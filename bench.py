@@ -334,7 +334,7 @@ def main_hp3d(args):
 
     # ---- dominant memory-bound kernel alone: SMPL-LBS (FK + skinning + joints)
     M = cbv * N
-    vp = torch.empty(M, 20670, device=dev).normal_()
+    vp = torch.empty(M, 20672, device=dev).normal_()
     Jt = torch.randn(cbv, 24, 3, device=dev)
     gR = hp.rot6d_to_rotmat(torch.randn(cbv, 6, device=dev))
     Rr = gb.local("rotmats")[:cbv].contiguous()

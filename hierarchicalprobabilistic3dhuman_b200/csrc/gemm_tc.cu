@@ -31,8 +31,9 @@ namespace {
 
 constexpr int KP = 224;              // padded K = 207 + 10 + 1 -> 224 (row pitch of the fp16 operands, 448 B)
 constexpr int KBLKS = 4;             // 64-wide k-blocks; the last one holds 32 valid columns
-constexpr int BM = 128, BN = 128;
-constexpr int TILE_BYTES = 128 * 64 * 2;   // 16 KB (A and B tiles alike)
+constexpr int BM = 128, BN = 128;          // (N = 256 tiles with 2 stages measured no faster: 1.00 vs 0.97 ms)
+constexpr int TILE_BYTES = BM * 64 * 2;    // A k-block tile: 16 KB
+constexpr int BTILE_BYTES = BN * 64 * 2;   // B k-block tile: 32 KB
 constexpr int STAGES = 4;
 constexpr int NPAD = 20736;          // 162 * 128
 
@@ -40,7 +41,7 @@ struct BlendArgs {
   int M, rep;
   int m_tiles, n_tiles, n_chunk, n_chunks;
   float inv_scale;
-  float* v_posed;          // [M][NV3]
+  float* v_posed;          // [M][VPITCH] (written through tmOut)
 };
 
 template <int PASSES>
@@ -48,8 +49,9 @@ struct BlendSmem {
   static constexpr int A_TILES = (PASSES == 3) ? 2 * KBLKS : KBLKS;
   static constexpr int A_OFFSET = 0;
   static constexpr int B_OFFSET = A_TILES * TILE_BYTES;
-  static constexpr int STG_OFFSET = B_OFFSET + STAGES * TILE_BYTES;     // epilogue transpose staging
-  static constexpr int STG_BYTES = 4 * 32 * 33 * 4;
+  static constexpr int STG_OFFSET = B_OFFSET + STAGES * BTILE_BYTES;    // epilogue transpose staging
+  static constexpr int STG_BYTES = 4 * 2 * 4096;                         // per epilogue warp: two 32x32 fp32 TMA-store tiles
+  static_assert(STG_OFFSET % 1024 == 0, "TMA store staging must be 1024-byte aligned (128B swizzle)");
   static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
@@ -78,7 +80,7 @@ template <int PASSES>
 __global__ void __launch_bounds__(256, 1)
 blend_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                 const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
-                const __grid_constant__ BlendArgs args) {
+                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ BlendArgs args) {
   using L = BlendSmem<PASSES>;
   extern __shared__ uint8_t smem_raw[];
   // pointer arithmetic on the extern array (not an integer round trip) keeps the shared address space visible to ptxas
@@ -127,8 +129,8 @@ blend_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
           for (int kb = 0; kb < KBLKS; ++kb)
             for (int part = 0; part < (PASSES == 3 ? 2 : 1); ++part) {
               mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-              if (elect_one()) mbar_arrive_expect_tx(&full_bar[stage], TILE_BYTES);
-              if (elect_one()) tma_load_2d(smem + L::B_OFFSET + stage * TILE_BYTES, part == 0 ? &tmBhi : &tmBlo, &full_bar[stage], kb * 64, nt * BN);
+              if (elect_one()) mbar_arrive_expect_tx(&full_bar[stage], BTILE_BYTES);
+              if (elect_one()) tma_load_2d(smem + L::B_OFFSET + stage * BTILE_BYTES, part == 0 ? &tmBhi : &tmBlo, &full_bar[stage], kb * 64, nt * BN);
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
       }
@@ -153,24 +155,25 @@ blend_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
           tc_fence_after_sync();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
           for (int kb = 0; kb < KBLKS; ++kb) {
-            const int nmma = (kb < KBLKS - 1) ? 4 : (KP - 64 * (KBLKS - 1)) / 16;   // 4,4,4,1
+            const int nmma = (kb < KBLKS - 1) ? 4 : (KP - 64 * (KBLKS - 1)) / 16;   // 4,4,4,2 (K = 224)
+            static_assert((KP - 64 * (KBLKS - 1)) / 16 == 2, "tail k-block must hold two K=16 steps");
             const uint64_t ahi = umma_desc_sw128(a_base + kb * TILE_BYTES);
             // B_hi[kb]:  A_hi B_hi (+ A_lo B_hi)
             mbar_wait(&full_bar[stage], phase, 3);
             tc_fence_after_sync();
-            uint64_t bd = umma_desc_sw128(b_base + stage * TILE_BYTES);
-            for (int k = 0; k < nmma; ++k) if (elect_one()) umma_f16(d_tmem, ahi + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            uint64_t bd = umma_desc_sw128(b_base + stage * BTILE_BYTES);
+            if (elect_one()) { if (nmma == 4) umma_f16_x4(d_tmem, ahi, bd, idesc, kb != 0 ? 1u : 0u); else umma_f16_x2(d_tmem, ahi, bd, idesc, 1u); }
             if (PASSES == 3) {
               const uint64_t alo = umma_desc_sw128(a_base + (KBLKS + kb) * TILE_BYTES);
-              for (int k = 0; k < nmma; ++k) if (elect_one()) umma_f16(d_tmem, alo + 2 * k, bd + 2 * k, idesc, 1u);
+              if (elect_one()) { if (nmma == 4) umma_f16_x4(d_tmem, alo, bd, idesc, 1u); else umma_f16_x2(d_tmem, alo, bd, idesc, 1u); }
             }
             if (elect_one()) umma_commit(&empty_bar[stage]);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             if (PASSES == 3) {   // B_lo[kb]:  A_hi B_lo
               mbar_wait(&full_bar[stage], phase, 3);
               tc_fence_after_sync();
-              bd = umma_desc_sw128(b_base + stage * TILE_BYTES);
-              for (int k = 0; k < nmma; ++k) if (elect_one()) umma_f16(d_tmem, ahi + 2 * k, bd + 2 * k, idesc, 1u);
+              bd = umma_desc_sw128(b_base + stage * BTILE_BYTES);
+              if (elect_one()) { if (nmma == 4) umma_f16_x4(d_tmem, ahi, bd, idesc, 1u); else umma_f16_x2(d_tmem, ahi, bd, idesc, 1u); }
               if (elect_one()) umma_commit(&empty_bar[stage]);
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -183,10 +186,12 @@ blend_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================================================== epilogue
+    // ===================================================== epilogue: TMEM -> registers -> (x inv_scale) -> 128B-swizzled
+    // 32x32 fp32 tile in shared memory -> one TMA store per tile chunk (fully coalesced, asynchronous, no LSU stores)
     const int ew = warp - 4;
-    float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET) + ew * 32 * 33;
+    uint8_t* stg_base = smem + L::STG_OFFSET + ew * 2 * 4096;
     int acc = 0; uint32_t acc_phase = 0;
+    int sbuf = 0;
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
       const int mt = u / args.n_chunks, chunk = u - mt * args.n_chunks;
       const int nt0 = chunk * args.n_chunk, nt1 = min(nt0 + args.n_chunk, args.n_tiles);
@@ -200,33 +205,32 @@ blend_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
           uint32_t r[32];
           tmem_ld_32x32(taddr + ch * 32, r);
           tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 32; ++c) stg[lane * 33 + c] = __uint_as_float(r[c]);
+          // the staging buffer used two chunks ago must have been read by its TMA store
+          if (lane == 0) tma_store_wait_read<1>();
           __syncwarp();
-          const int n = nt * BN + ch * 32 + lane;
-          if (n < NV3) {
-            float* dst = args.v_posed + (size_t)m_base * NV3 + n;
-            const int rows = args.M - m_base;
-            if (rows >= 32) {                         // full tile: batch the shared-memory reads, then the stores
+          float4* row = reinterpret_cast<float4*>(stg_base + sbuf * 4096 + lane * 128);
 #pragma unroll
-              for (int r0 = 0; r0 < 32; r0 += 8) {
-                float v[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = stg[(r0 + e) * 33 + lane] * args.inv_scale;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) dst[(size_t)(r0 + e) * NV3] = v[e];
-              }
-            } else {
-              for (int rr = 0; rr < rows; ++rr) dst[(size_t)rr * NV3] = stg[rr * 33 + lane] * args.inv_scale;
-            }
+          for (int q = 0; q < 8; ++q) {
+            float4 v;
+            v.x = __uint_as_float(r[4 * q]) * args.inv_scale; v.y = __uint_as_float(r[4 * q + 1]) * args.inv_scale;
+            v.z = __uint_as_float(r[4 * q + 2]) * args.inv_scale; v.w = __uint_as_float(r[4 * q + 3]) * args.inv_scale;
+            row[q ^ (lane & 7)] = v;                       // 128B swizzle: 16-byte chunk index XOR (row & 7)
           }
+          fence_proxy_async();
           __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmOut, stg_base + sbuf * 4096, nt * BN + ch * 32, m_base);   // rows >= M / cols >= pitch are clipped
+            tma_store_commit();
+          }
+          sbuf ^= 1;
         }
         tc_fence_before_sync();
         mbar_arrive(&tmem_empty[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+    if (lane == 0) tma_store_wait_all();
+    __syncwarp();
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -319,15 +323,18 @@ int blend_tc_forward(void* p, const float* betas, int Mb, const float* body_pose
   a.m_tiles = cdiv(M, BM); a.n_tiles = NPAD / BN;
   a.n_chunk = 18; a.n_chunks = cdiv(a.n_tiles, a.n_chunk);
   a.inv_scale = h->inv_scale; a.v_posed = v_posed;
+  CUtensorMap tmOut;
+  rc = make_tmap_f32_2d(&tmOut, v_posed, VPITCH, (uint64_t)M, (uint64_t)VPITCH * 4, 32, 32);
+  if (rc) return rc;
   const int grid = std::min(a.m_tiles * a.n_chunks, h->num_sms);
   if (h->passes == 3) {
     static bool set = false;
     if (!set) { HP3D_CUDA(cudaFuncSetAttribute(blend_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, BlendSmem<3>::TOTAL)); set = true; }
-    blend_tc_kernel<3><<<grid, 256, BlendSmem<3>::TOTAL, stream>>>(tmAhi, tmAlo, h->tmBhi, h->tmBlo, a);
+    blend_tc_kernel<3><<<grid, 256, BlendSmem<3>::TOTAL, stream>>>(tmAhi, tmAlo, h->tmBhi, h->tmBlo, tmOut, a);
   } else {
     static bool set = false;
     if (!set) { HP3D_CUDA(cudaFuncSetAttribute(blend_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BlendSmem<1>::TOTAL)); set = true; }
-    blend_tc_kernel<1><<<grid, 256, BlendSmem<1>::TOTAL, stream>>>(tmAhi, tmAlo, h->tmBhi, h->tmBlo, a);
+    blend_tc_kernel<1><<<grid, 256, BlendSmem<1>::TOTAL, stream>>>(tmAhi, tmAlo, h->tmBhi, h->tmBlo, tmOut, a);
   }
   return launch_status("blend_tc_kernel");
 }

@@ -4,7 +4,7 @@
 // Replaces reference models/smpl_official.py:27-41 and the smplx 0.1.26 lbs() it calls
 // (SURVEY.md §8c steps 1-9). Data layout in HBM (all fp32):
 //   v_shaped  [Mb][20672]   one row per distinct shape (pitch padded to 16 B)
-//   v_posed   [M][20670]    written by the blend stage, read once by the LBS kernel
+//   v_posed   [M][20672]    written by the blend stage (TMA stores: 16-byte row pitch), read once by the LBS kernel
 //   vertices  [M][6890][3]  the reference's output layout; joints [M][90][3]
 // Model constants are repacked once at create time:
 //   shapedirs -> [10][20672]; posedirs -> [207][20672] (row pitch padded for float4 loads);
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256) pose_blend_fp32_kernel(const float* __res
     const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
     if (m >= M) continue;
     const float* vs = v_shaped + (size_t)(m / rep) * VPITCH;
-    float* out = v_posed + (size_t)m * NV3;
+    float* out = v_posed + (size_t)m * VPITCH;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int n = n0 + h * 64 + tx * 4;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256) lbs_kernel(const float* __restrict__ v_po
       }
     }
     __syncthreads();
-    const float* vp = v_posed + (size_t)m * NV3;
+    const float* vp = v_posed + (size_t)m * VPITCH;
     float* vo = vertices + (size_t)m * NV3;
     for (int v = tid; v < NV; v += blockDim.x) {
       const float x = vp[3 * v], y = vp[3 * v + 1], z = vp[3 * v + 2];
@@ -309,14 +309,14 @@ __device__ __forceinline__ void lbs_tile_body(const LbsTileCtx& c) {
     joff[q] = c.tile_joff[tile * NQCAP + q];
   }
   const size_t voff = (size_t)3 * v0;
-  const float* src0 = c.v_posed + (size_t)c.m0 * NV3 + voff;
+  const float* src0 = c.v_posed + (size_t)c.m0 * VPITCH + voff;
   float* dst0 = c.vertices + (size_t)c.m0 * NV3 + voff;
   const int Gv = c.Gv;
   float2 pa[3], pb[3], na[3], nb[3];
   auto ld = [&](int g, float2 (&p)[3]) {
     p[0] = p[1] = p[2] = make_float2(0.f, 0.f);
     if (valid && g < Gv) {
-      const float* s_ = src0 + (size_t)g * NV3;
+      const float* s_ = src0 + (size_t)g * VPITCH;
       p[0] = *reinterpret_cast<const float2*>(s_);
       p[1] = *reinterpret_cast<const float2*>(s_ + 2);
       p[2] = *reinterpret_cast<const float2*>(s_ + 4);
@@ -377,6 +377,8 @@ __global__ void __launch_bounds__(256, 2) lbs_tile_kernel(const float* __restric
   __shared__ float4 sA[LBS_G][NJ * 3];
   __shared__ float sV[LBS_G][NU_MAX][3];                               // parked vertices for the joint epilogue
   float (*sG)[NJ][12] = reinterpret_cast<float (*)[NJ][12]>(&sV[0][0][0]);   // FK scratch (phase 1) aliases sV
+  __shared__ int next_tile;
+  if (threadIdx.x == 0) next_tile = 0;
   static_assert(sizeof(float) * LBS_G * NJ * 12 <= sizeof(float) * LBS_G * NU_MAX * 3, "FK scratch must fit");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int repb = M / Mb, repg = M / Mg;
@@ -432,7 +434,12 @@ __global__ void __launch_bounds__(256, 2) lbs_tile_kernel(const float* __restric
   __syncthreads();
   // ---- phase 2: skinning, warp sweeps its tiles, meshes innermost. The tile's joint count is warp-uniform:
   // dispatch once per tile to a fully unrolled, branch-free body for exactly that count.
-  for (int tile = warp; tile < NT; tile += 8) {
+  // tiles cost between 1 and 8(12) joints: warps take the next unprocessed tile from a CTA-wide counter
+  for (;;) {
+    int tile = 0;
+    if (lane == 0) tile = atomicAdd(&next_tile, 1);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= NT) break;
     const int nq = tile_nq[tile];
     LbsTileCtx c;
     c.tile = tile; c.lane = lane; c.m0 = m0; c.Gv = Gv; c.v_posed = v_posed; c.vertices = vertices;
@@ -783,7 +790,7 @@ extern "C" void hp3d_smpl_destroy(hp3d_smpl* h) {
 
 static size_t ws_vshaped(int Mb) { return align_up((size_t)Mb * VPITCH * sizeof(float), 256); }
 static size_t ws_J(int Mb) { return align_up((size_t)Mb * NJ * 3 * sizeof(float), 256); }
-static size_t ws_vposed(int M) { return align_up((size_t)M * NV3 * sizeof(float), 256); }
+static size_t ws_vposed(int M) { return align_up((size_t)M * VPITCH * sizeof(float), 1024); }
 
 extern "C" size_t hp3d_smpl_pose_blend_workspace_bytes(int M) { return M > 0 ? blend_tc_workspace_bytes(M) : 0; }
 

@@ -86,6 +86,18 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// TMA store (shared -> global, bulk-group completion): one thread issues; the shared-memory source must have been
+// written with generic stores followed by fence_proxy_async().
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMEM + tcgen05
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {   // whole warp
@@ -122,6 +134,17 @@ __device__ __forceinline__ void umma_f16_x4(uint32_t tmem_d, uint64_t desc_a, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, 1;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, 1;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, 1;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc0)
+      : "memory");
+}
+// Two K=16 steps (a 32-wide k-block tail).
+__device__ __forceinline__ void umma_f16_x2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t acc0) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 a1, b1;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "add.u64 a1, %1, 2;\n\tadd.u64 b1, %2, 2;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, 1;\n\t}" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(acc0)
       : "memory");
 }
@@ -181,6 +204,18 @@ inline EncodeTiledFn encode_fn() {
       fn = (EncodeTiledFn)p;
   }
   return fn;
+}
+
+// fp32 2-D tensor map (rows x cols, row pitch in bytes), box {box_cols, box_rows}, 128B swizzle: used for TMA stores.
+inline int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_bytes,
+                            uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return -3; }
+  cuuint64_t gd[2] = {cols, rows}; cuuint64_t gs[1] = {pitch_bytes}; cuuint32_t bx[2] = {box_cols, box_rows}; cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(fp32) failed with CUresult %d", (int)r); return -3; }
+  return 0;
 }
 
 // fp16 tensor, `rank` dims (innermost first), byte strides for dims 1..rank-1, 128B swizzle, zero OOB fill.

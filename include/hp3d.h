@@ -62,7 +62,7 @@ int hp3d_smpl_shape_blend(const hp3d_smpl* h, const float* betas, int Mb, float*
                           float* J /*[Mb*24*3]*/, void* stream);
 size_t hp3d_smpl_pose_blend_workspace_bytes(int M);   /* fp16 hi/lo pose features for the tensor-core blend */
 int hp3d_smpl_pose_blend(const hp3d_smpl* h, const float* betas, const float* v_shaped, int Mb, const float* body_pose,
-                         int M, float* v_posed /*[M*20670]*/, void* workspace, size_t workspace_bytes, void* stream);
+                         int M, float* v_posed /*[M*20672], row pitch 20672 floats*/, void* workspace, size_t workspace_bytes, void* stream);
 int hp3d_smpl_lbs(const hp3d_smpl* h, const float* v_posed, const float* J, int Mb, const float* global_orient,
                   int Mg, const float* body_pose, int M, float* vertices, float* joints, void* stream);
 /* smplx batch_rodrigues: axis-angle [n*3] -> rotmats [n*9] (pose2rot=True callers:

@@ -11,7 +11,7 @@ M = B * N
 dev = torch.device("cuda", 0)
 smpl = hp.SMPL(model=syn.synthetic_smpl_model()).to(dev)
 L = _lib.lib(); h = smpl._handle(dev)
-vp = torch.empty(M, 20670, device=dev).normal_()
+vp = torch.empty(M, 20672, device=dev).normal_()
 J = torch.randn(B, 24, 3, device=dev)
 gR = hp.rot6d_to_rotmat(torch.randn(B, 6, device=dev))
 R = hp.rot6d_to_rotmat(torch.randn(M * 23, 6, device=dev)).view(M, 23, 3, 3)
