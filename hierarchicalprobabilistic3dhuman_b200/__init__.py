@@ -12,10 +12,12 @@ All arithmetic runs in hand-written CUDA behind the C ABI of include/hp3d.h (lib
 from .pose_net import PoseMFShapeGaussianNet
 from .smpl import SMPL, SMPLOutput
 from .sampling import (pose_matrix_fisher_sampling_torch, compute_vertex_uncertainties_by_poseMF_shapeGaussian_sampling,
-                       sample_meshes_batched, vertex_uncertainty)
+                       sample_meshes_batched, vertex_uncertainty, rank_samples_by_joints2d,
+                       joints2D_error_sorted_verts_sampling)
 from .rigid import rot6d_to_rotmat
 from .pipeline import HotPathPipeline
 
 __all__ = ["PoseMFShapeGaussianNet", "SMPL", "SMPLOutput", "pose_matrix_fisher_sampling_torch",
            "compute_vertex_uncertainties_by_poseMF_shapeGaussian_sampling", "sample_meshes_batched",
-           "vertex_uncertainty", "rot6d_to_rotmat", "HotPathPipeline"]
+           "vertex_uncertainty", "rot6d_to_rotmat", "HotPathPipeline", "rank_samples_by_joints2d",
+           "joints2D_error_sorted_verts_sampling"]

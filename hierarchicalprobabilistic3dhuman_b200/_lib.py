@@ -12,7 +12,7 @@ EXPORTS = [
     "hp3d_version", "hp3d_last_error",
     "hp3d_smpl_create", "hp3d_smpl_destroy", "hp3d_smpl_workspace_bytes", "hp3d_smpl_forward",
     "hp3d_smpl_shape_blend", "hp3d_smpl_pose_blend_workspace_bytes", "hp3d_smpl_pose_blend", "hp3d_smpl_lbs", "hp3d_rodrigues", "hp3d_rot6d_to_rotmat",
-    "hp3d_vertex_uncertainty", "hp3d_mf_sample",
+    "hp3d_vertex_uncertainty", "hp3d_rank_samples_by_joints2d", "hp3d_mf_sample",
     "hp3d_head_create", "hp3d_head_destroy", "hp3d_head_workspace_bytes", "hp3d_head_forward",
     "hp3d_encoder_create", "hp3d_encoder_destroy", "hp3d_encoder_workspace_bytes", "hp3d_encoder_forward", "hp3d_encoder_forward_taps",
 ]
@@ -83,6 +83,8 @@ def lib():
     L.hp3d_encoder_workspace_bytes.argtypes = [c_void_p, c_int, c_int, c_int]
     L.hp3d_encoder_forward.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
     L.hp3d_encoder_forward_taps.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]
+    L.hp3d_rank_samples_by_joints2d.argtypes = [c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_float,
+                                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     _lib = L
     return L
 

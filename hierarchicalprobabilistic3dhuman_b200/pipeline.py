@@ -48,10 +48,10 @@ class HotPathPipeline:
         self._stage = None
         self._slot = 0
         # kernels launched by one pass (ResNet-18 fast mode 23, head 6, rot6d 1, SMPL 4+4, sampler 1, stats 1, betas copy 1)
-        self.launches_per_pass = 23 + 6 + 1 + 4 + 1 + (4 + 1) * len(self.vertex_chunks) + 1
+        self.launches_per_pass = 23 + 6 + 1 + 4 + 1 + (4 + 1) * len(self.vertex_chunks) + 1 + 2
 
     # ------------------------------------------------------------------ device-resident pass
-    def _after_encoder(self, feats):
+    def _after_encoder(self, feats, proxy_rep=None):
         L, B, N = self.L, self.B, self.N
         F, U, S, V, mode, shape_params, glob, cam = self.net.head(feats)
         loc = shape_params[:, :10].contiguous()
@@ -70,13 +70,18 @@ class HotPathPipeline:
                                                  _lib.stream_ptr()), "hp3d_vertex_uncertainty")
             if self.on_vertices_chunk is not None:
                 self.on_vertices_chunk(c)
-        return dict(mode_vertices=out_mode.vertices, mode_joints=out_mode.joints, joints=self.joints, rotmats=R,
-                    uncertainty=self.uncertainty, vertices=self.vertices, betas=self.betas, pose_S=S, cam=cam)
+        res = dict(mode_vertices=out_mode.vertices, mode_joints=out_mode.joints, joints=self.joints, rotmats=R,
+                   uncertainty=self.uncertainty, vertices=self.vertices, betas=self.betas, pose_S=S, cam=cam)
+        if proxy_rep is not None:     # rank the N samples of every image by 2D-joint consistency (sampling_utils.py:195-233)
+            from .sampling import rank_samples_by_joints2d
+            rk = rank_samples_by_joints2d(self.joints.view(B, N, 90, 3), proxy_rep, cam)
+            res["sample_order"], res["sample_error"] = rk["order"], rk["error"]
+        return res
 
     def run_device(self, x_dev):
         """x_dev (B,18,256,256) fp32 on the GPU -> dict of device tensors (sample vertices live in `vertices`)."""
         with torch.cuda.device(self.dev):
-            return self._after_encoder(self.net.encode(x_dev))
+            return self._after_encoder(self.net.encode(x_dev), x_dev)
 
     # ------------------------------------------------------------------ host-streaming pass
     def _staging(self, x_host):
@@ -123,7 +128,7 @@ class HotPathPipeline:
             st["x_free"][slot] = free
             if st["out_done"][slot ^ 1] is not None:
                 main.wait_event(st["out_done"][slot ^ 1])               # previous call's results have left the device buffers
-            res = self._after_encoder(torch.cat(feats) if C > 1 else feats[0])
+            res = self._after_encoder(torch.cat(feats) if C > 1 else feats[0], xbuf)
             done = torch.cuda.Event()
             done.record(main)
             out = st["out"][slot]

@@ -74,6 +74,15 @@ int hp3d_rot6d_to_rotmat(const float* x6, int n, float* rotmats, void* stream);
  * vertices [B*N*6890*3] -> mean_vertices [B*6890*3] (may be NULL), avg_dist [B*6890] */
 int hp3d_vertex_uncertainty(const float* vertices, int B, int N, float* mean_vertices, float* avg_dist, void* stream);
 
+/* sample ranking by 2D-joint consistency, replaces utils/sampling_utils.py:195-233 batched over B images:
+ * joints [B*N*90*3]; heatmaps = pointer to the FIRST of 17 joint heat-maps (H*W floats each) of image 0, consecutive
+ * images `heatmap_image_stride` floats apart (for a (B,18,H,W) proxy representation: base + H*W, stride 18*H*W);
+ * cam [B*3] weak-perspective (s,tx,ty). Outputs: order [B*N] sample indices by ascending error, err [B*N] (max pixel
+ * distance over visible COCO joints), joints2d_out [B*17*2] heat-map arg-max (x,y; -1 if invisible), vis_out [B*17]. */
+int hp3d_rank_samples_by_joints2d(const float* joints, const float* heatmaps, long long heatmap_image_stride,
+                                  const float* cam, int B, int N, int H, int W, float eps, int32_t* order, float* err,
+                                  float* joints2d_out, int32_t* vis_out, void* stream);
+
 /* ---------------------------------------------------------------- matrix-Fisher sampler
  * replaces: utils/sampling_utils.py:74-143 (pose_matrix_fisher_sampling_torch) incl. :10-71
  * (bingham_sampling_for_matrix_fisher_torch) and utils/rigid_transform_utils.py:113-133.

@@ -65,3 +65,20 @@ def test_sampler_oracle_matches_reference_golden():
         assert (torch.det(R) - 1).abs().max() < 1e-5
         eye = torch.eye(3)
         assert (R.transpose(-1, -2) @ R - eye).abs().max() < 1e-5
+
+
+def test_sample_ranking_helpers_match_reference_golden():
+    """heat-map arg-max and projection helpers vs outputs of the reference's own functions."""
+    g = load_golden("rank_helpers")
+    x = torch.from_numpy(syn.synthetic_proxy_rep(3, seed=int(g["proxy_seed"])))
+    j2d, vis = sampler_oracle.heatmaps_to_joints2d(x[:, 1:])
+    assert torch.equal(j2d, torch.from_numpy(g["joints2d"])) and torch.equal(vis, torch.from_numpy(g["vis"]))
+    px = sampler_oracle.project_joints_to_pixels(torch.from_numpy(g["J"]), torch.from_numpy(g["cam"]), 256)
+    assert torch.equal(px, torch.from_numpy(g["pixels"]))
+    # ranking is a permutation sorted by error
+    rs = np.random.RandomState(1)
+    joints = torch.from_numpy(rs.normal(0, 0.4, size=(3, 11, 90, 3)).astype(np.float32))
+    cam = torch.tensor([[0.9, 0.0, 0.0]]).expand(3, -1)
+    order, err = sampler_oracle.rank_samples(joints, x[:, 1:], cam)
+    assert all(sorted(o.tolist()) == list(range(11)) for o in order)
+    assert (torch.gather(err, 1, order).diff(dim=1) >= 0).all()
