@@ -43,7 +43,9 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
   n0 = r * c; n1 = r * s;
 }
 
-__global__ void __launch_bounds__(768) mf_sample_kernel(const float* __restrict__ U, const float* __restrict__ S,
+// Two CTAs per SM (2 x 23 warps = 72 % of the SM's warp slots): the per-joint frames U_p, V_p are only needed by
+// the conversion step, so they live in shared memory and the rejection loop keeps ~20 live registers.
+__global__ void __launch_bounds__(768, 2) mf_sample_kernel(const float* __restrict__ U, const float* __restrict__ S,
                                                          const float* __restrict__ V, int B, int J, int N, float b,
                                                          float m_star, uint64_t seed, uint64_t offset,
                                                          const float* __restrict__ eps_in,
@@ -55,11 +57,13 @@ __global__ void __launch_bounds__(768) mf_sample_kernel(const float* __restrict_
   const int tile_stride = J * 9;
   float* tile = smem;                                  // [CHUNK][J*9]
   float4* stage = reinterpret_cast<float4*>(smem + CHUNK * tile_stride) + warp * 64;   // [64] quats per warp
+  float* frames = smem + CHUNK * tile_stride + J * 64 * 4 + warp * 20;                   // U_p [9] | V_p [9] per warp
   for (int img = blockIdx.x; img < B; img += gridDim.x) {
     const size_t ij = (size_t)img * J + j;
     // ---- proper SVD factors and envelope parameters (warp-uniform, held by every lane)
-    float Up[9], Vp[9], s0, s1, s2;
+    float s0, s1, s2;
     {
+      float Up[9], Vp[9];
       const float* u = U + ij * 9; const float* v = V + ij * 9; const float* s = S + ij * 3;
 #pragma unroll
       for (int e = 0; e < 9; ++e) { Up[e] = u[e]; Vp[e] = v[e]; }
@@ -70,13 +74,18 @@ __global__ void __launch_bounds__(768) mf_sample_kernel(const float* __restrict_
       s0 = s[0]; s1 = s[1]; s2 = s[2] * (du * dv);
       Up[2] *= du; Up[5] *= du; Up[8] *= du;
       Vp[2] *= dv; Vp[5] *= dv; Vp[8] *= dv;
+      if (lane == 0) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) { frames[e] = Up[e]; frames[9 + e] = Vp[e]; }
+      }
+      __syncwarp();
     }
     const float A1 = 2.f * (s1 + s2), A2 = 2.f * (s0 + s2), A3 = 2.f * (s0 + s1);      // A0 = 0
     const float O0 = 1.f, O1 = 1.f + 2.f * A1 / b, O2 = 1.f + 2.f * A2 / b, O3 = 1.f + 2.f * A3 / b;
     // torch.pow(x, -0.5) on CPU is 1/sqrt(x) (both IEEE-rounded), reference :124
     const float g0 = 1.f, g1 = 1.0f / sqrtf(O1), g2 = 1.0f / sqrtf(O2), g3 = 1.0f / sqrtf(O3);
     int have = 0, round = 0;
-    unsigned long long n_prop = 0, n_acc = 0, n_fail = 0;
+    unsigned n_prop = 0, n_acc = 0, n_fail = 0;
     for (int n0 = 0; n0 < N; n0 += CHUNK) {
       const int need = min(CHUNK, N - n0);
       while (have < need) {
@@ -138,6 +147,9 @@ __global__ void __launch_bounds__(768) mf_sample_kernel(const float* __restrict_
         float Rq[9] = {w2 + x2 - y2 - z2, 2 * xy - 2 * wz, 2 * wy + 2 * xz,
                        2 * wz + 2 * xy, w2 - x2 + y2 - z2, 2 * yz - 2 * wx,
                        2 * xz - 2 * wy, 2 * wx + 2 * yz, w2 - x2 - y2 + z2};
+        float Up[9], Vp[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) { Up[e] = frames[e]; Vp[e] = frames[9 + e]; }
         float T[9];    // Rq * Vp^T
 #pragma unroll
         for (int r = 0; r < 3; ++r)
@@ -168,8 +180,8 @@ __global__ void __launch_bounds__(768) mf_sample_kernel(const float* __restrict_
       __syncthreads();
     }
     if (stats && lane == 0) {
-      atomicAdd(stats + 0, n_prop); atomicAdd(stats + 1, n_acc);
-      if (n_fail) atomicAdd(stats + 2, n_fail);
+      atomicAdd(stats + 0, (unsigned long long)n_prop); atomicAdd(stats + 1, (unsigned long long)n_acc);
+      if (n_fail) atomicAdd(stats + 2, (unsigned long long)n_fail);
     }
   }
 }
@@ -185,7 +197,7 @@ extern "C" int hp3d_mf_sample(const float* U, const float* S, const float* V, in
   HP3D_ARG((eps == nullptr) == (w == nullptr), "eps and w must be given together");
   HP3D_ARG(!eps || oversampling > 0, "oversampling must be > 0 with injected noise");
   const float m_star = (float)(exp(-(4.0 - (double)b) / 2.0) * (4.0 / (double)b) * (4.0 / (double)b));
-  const size_t smem = (size_t)CHUNK * J * 9 * sizeof(float) + (size_t)J * 64 * sizeof(float4);
+  const size_t smem = (size_t)CHUNK * J * 9 * sizeof(float) + (size_t)J * 64 * sizeof(float4) + (size_t)J * 20 * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     HP3D_CUDA(cudaFuncSetAttribute(mf_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));

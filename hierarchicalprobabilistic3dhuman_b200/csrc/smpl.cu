@@ -284,7 +284,8 @@ constexpr int TV = 64;                      // vertices per tile
 constexpr int NT = (NV + TV - 1) / TV;      // 108
 constexpr int NQCAP = 12;
 constexpr int LBS_G = 8;                    // meshes per CTA (== warps per CTA)
-constexpr int NU_MAX = NPICK + 255;         // unique vertices feeding the 66 extra joints (<= 276)
+constexpr int NU_MAX = NPICK + 255;
+constexpr int LBS_DEFAULT_MODE = 1;         // see hp3d_smpl_lbs         // unique vertices feeding the 66 extra joints (<= 276)
 
 struct LbsTileCtx {
   int tile, lane, m0, Gv, park0, park1;
@@ -294,8 +295,22 @@ struct LbsTileCtx {
   float* sV;            // [LBS_G][NU_MAX][3]
 };
 
+// Packed fp32 FMA (Blackwell FFMA2): acc.xy += s * v.xy in ONE issue slot; ptxas encodes the scalar as a
+// broadcast operand (FFMA2 R, R.F32, R.F32x2, R.F32x2), so (s,s) costs no extra register.
+__device__ __forceinline__ void ffma2(float2& acc, float s, float x, float y) {
+  unsigned long long a, b, c, d;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(s));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(x), "f"(y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc.x), "f"(acc.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(d));
+}
+
 // One 64-vertex tile x Gv meshes with exactly NQ joints (compile-time): no per-joint predicates or branches.
-template <int NQ>
+// F2: blend the joint transforms with packed FFMA2 (halves the FMA issue slots, the kernel's dominant
+// instruction); PF: meshes whose vertex loads are in flight ahead of the one being skinned (bytes in flight
+// per warp = PF x 768 B).
+template <int NQ, bool F2, int PF>
 __device__ __forceinline__ void lbs_tile_body(const LbsTileCtx& c) {
   const int lane = c.lane, tile = c.tile;
   const int v0 = tile * TV + 2 * lane;
@@ -312,7 +327,6 @@ __device__ __forceinline__ void lbs_tile_body(const LbsTileCtx& c) {
   const float* src0 = c.v_posed + (size_t)c.m0 * VPITCH + voff;
   float* dst0 = c.vertices + (size_t)c.m0 * NV3 + voff;
   const int Gv = c.Gv;
-  float2 pa[3], pb[3], na[3], nb[3];
   auto ld = [&](int g, float2 (&p)[3]) {
     p[0] = p[1] = p[2] = make_float2(0.f, 0.f);
     if (valid && g < Gv) {
@@ -322,20 +336,8 @@ __device__ __forceinline__ void lbs_tile_body(const LbsTileCtx& c) {
       p[2] = *reinterpret_cast<const float2*>(s_ + 4);
     }
   };
-  auto skin = [&](int g, const float2 (&p)[3]) {
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, b0 = a0, b1 = a0, b2 = a0;
-    const float4* Ag = c.sA + g * (NJ * 3);
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const float4 r0 = Ag[joff[q]], r1 = Ag[joff[q] + 1], r2 = Ag[joff[q] + 2];
-      const float u = w0[q], v = w1[q];
-      a0.x = fmaf(u, r0.x, a0.x); a0.y = fmaf(u, r0.y, a0.y); a0.z = fmaf(u, r0.z, a0.z); a0.w = fmaf(u, r0.w, a0.w);
-      a1.x = fmaf(u, r1.x, a1.x); a1.y = fmaf(u, r1.y, a1.y); a1.z = fmaf(u, r1.z, a1.z); a1.w = fmaf(u, r1.w, a1.w);
-      a2.x = fmaf(u, r2.x, a2.x); a2.y = fmaf(u, r2.y, a2.y); a2.z = fmaf(u, r2.z, a2.z); a2.w = fmaf(u, r2.w, a2.w);
-      b0.x = fmaf(v, r0.x, b0.x); b0.y = fmaf(v, r0.y, b0.y); b0.z = fmaf(v, r0.z, b0.z); b0.w = fmaf(v, r0.w, b0.w);
-      b1.x = fmaf(v, r1.x, b1.x); b1.y = fmaf(v, r1.y, b1.y); b1.z = fmaf(v, r1.z, b1.z); b1.w = fmaf(v, r1.w, b1.w);
-      b2.x = fmaf(v, r2.x, b2.x); b2.y = fmaf(v, r2.y, b2.y); b2.z = fmaf(v, r2.z, b2.z); b2.w = fmaf(v, r2.w, b2.w);
-    }
+  auto emit = [&](int g, const float2 (&p)[3], const float4& a0, const float4& a1, const float4& a2,
+                  const float4& b0, const float4& b1, const float4& b2) {
     if (valid) {
       const float x0 = p[0].x, y0 = p[0].y, z0 = p[1].x, x1 = p[1].y, y1 = p[2].x, z1 = p[2].y;
       float2 o0, o1, o2;
@@ -353,17 +355,59 @@ __device__ __forceinline__ void lbs_tile_body(const LbsTileCtx& c) {
       if (c.park1 >= 0) { float* sv = c.sV + ((size_t)g * NU_MAX + c.park1) * 3; sv[0] = o1.y; sv[1] = o2.x; sv[2] = o2.y; }
     }
   };
-  ld(0, pa); ld(1, pb);
-  for (int g = 0; g < Gv; g += 2) {
-    ld(g + 2, na); ld(g + 3, nb);
-    skin(g, pa);
-    if (g + 1 < Gv) skin(g + 1, pb);
+  auto skin = [&](int g, const float2 (&p)[3]) {
+    const float4* Ag = c.sA + g * (NJ * 3);
+    if constexpr (F2) {
+      float2 a[6], b[6];                               // rows 0..2 as (xy, zw) pairs, vertex 0 / vertex 1
 #pragma unroll
-    for (int e = 0; e < 3; ++e) { pa[e] = na[e]; pb[e] = nb[e]; }
+      for (int e = 0; e < 6; ++e) a[e] = b[e] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const float4 r0 = Ag[joff[q]], r1 = Ag[joff[q] + 1], r2 = Ag[joff[q] + 2];
+        const float u = w0[q], v = w1[q];
+        ffma2(a[0], u, r0.x, r0.y); ffma2(a[1], u, r0.z, r0.w);
+        ffma2(a[2], u, r1.x, r1.y); ffma2(a[3], u, r1.z, r1.w);
+        ffma2(a[4], u, r2.x, r2.y); ffma2(a[5], u, r2.z, r2.w);
+        ffma2(b[0], v, r0.x, r0.y); ffma2(b[1], v, r0.z, r0.w);
+        ffma2(b[2], v, r1.x, r1.y); ffma2(b[3], v, r1.z, r1.w);
+        ffma2(b[4], v, r2.x, r2.y); ffma2(b[5], v, r2.z, r2.w);
+      }
+      emit(g, p, make_float4(a[0].x, a[0].y, a[1].x, a[1].y), make_float4(a[2].x, a[2].y, a[3].x, a[3].y),
+           make_float4(a[4].x, a[4].y, a[5].x, a[5].y), make_float4(b[0].x, b[0].y, b[1].x, b[1].y),
+           make_float4(b[2].x, b[2].y, b[3].x, b[3].y), make_float4(b[4].x, b[4].y, b[5].x, b[5].y));
+    } else {
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, b0 = a0, b1 = a0, b2 = a0;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const float4 r0 = Ag[joff[q]], r1 = Ag[joff[q] + 1], r2 = Ag[joff[q] + 2];
+        const float u = w0[q], v = w1[q];
+        a0.x = fmaf(u, r0.x, a0.x); a0.y = fmaf(u, r0.y, a0.y); a0.z = fmaf(u, r0.z, a0.z); a0.w = fmaf(u, r0.w, a0.w);
+        a1.x = fmaf(u, r1.x, a1.x); a1.y = fmaf(u, r1.y, a1.y); a1.z = fmaf(u, r1.z, a1.z); a1.w = fmaf(u, r1.w, a1.w);
+        a2.x = fmaf(u, r2.x, a2.x); a2.y = fmaf(u, r2.y, a2.y); a2.z = fmaf(u, r2.z, a2.z); a2.w = fmaf(u, r2.w, a2.w);
+        b0.x = fmaf(v, r0.x, b0.x); b0.y = fmaf(v, r0.y, b0.y); b0.z = fmaf(v, r0.z, b0.z); b0.w = fmaf(v, r0.w, b0.w);
+        b1.x = fmaf(v, r1.x, b1.x); b1.y = fmaf(v, r1.y, b1.y); b1.z = fmaf(v, r1.z, b1.z); b1.w = fmaf(v, r1.w, b1.w);
+        b2.x = fmaf(v, r2.x, b2.x); b2.y = fmaf(v, r2.y, b2.y); b2.z = fmaf(v, r2.z, b2.z); b2.w = fmaf(v, r2.w, b2.w);
+      }
+      emit(g, p, a0, a1, a2, b0, b1, b2);
+    }
+  };
+  float2 cur[PF][3], nxt[PF][3];
+#pragma unroll
+  for (int i = 0; i < PF; ++i) ld(i, cur[i]);
+  for (int g = 0; g < Gv; g += PF) {
+#pragma unroll
+    for (int i = 0; i < PF; ++i) ld(g + PF + i, nxt[i]);
+#pragma unroll
+    for (int i = 0; i < PF; ++i)
+      if (g + i < Gv) skin(g + i, cur[i]);
+#pragma unroll
+    for (int i = 0; i < PF; ++i)
+#pragma unroll
+      for (int e = 0; e < 3; ++e) cur[i][e] = nxt[i][e];
   }
 }
 
-template <int NQMAX>
+template <int NQMAX, bool F2, int PF>
 __global__ void __launch_bounds__(256, 2) lbs_tile_kernel(const float* __restrict__ v_posed, const float* __restrict__ J,
                                                           int Mb, const float* __restrict__ global_orient, int Mg,
                                                           const float* __restrict__ body_pose, int M,
@@ -452,21 +496,21 @@ __global__ void __launch_bounds__(256, 2) lbs_tile_kernel(const float* __restric
       }
     }
     switch (nq) {
-      case 1: lbs_tile_body<1>(c); break;
-      case 2: lbs_tile_body<2>(c); break;
-      case 3: lbs_tile_body<3>(c); break;
-      case 4: lbs_tile_body<4>(c); break;
-      case 5: lbs_tile_body<5>(c); break;
-      case 6: lbs_tile_body<6>(c); break;
-      case 7: lbs_tile_body<7>(c); break;
-      case 8: lbs_tile_body<8>(c); break;
+      case 1: lbs_tile_body<1, F2, PF>(c); break;
+      case 2: lbs_tile_body<2, F2, PF>(c); break;
+      case 3: lbs_tile_body<3, F2, PF>(c); break;
+      case 4: lbs_tile_body<4, F2, PF>(c); break;
+      case 5: lbs_tile_body<5, F2, PF>(c); break;
+      case 6: lbs_tile_body<6, F2, PF>(c); break;
+      case 7: lbs_tile_body<7, F2, PF>(c); break;
+      case 8: lbs_tile_body<8, F2, PF>(c); break;
       default:
         if constexpr (NQMAX > 8) {
           switch (nq) {
-            case 9: lbs_tile_body<9>(c); break;
-            case 10: lbs_tile_body<10>(c); break;
-            case 11: lbs_tile_body<11>(c); break;
-            case 12: lbs_tile_body<12>(c); break;
+            case 9: lbs_tile_body<9, F2, PF>(c); break;
+            case 10: lbs_tile_body<10, F2, PF>(c); break;
+            case 11: lbs_tile_body<11, F2, PF>(c); break;
+            case 12: lbs_tile_body<12, F2, PF>(c); break;
             default: break;
           }
         }
@@ -838,15 +882,26 @@ extern "C" int hp3d_smpl_lbs(const hp3d_smpl* h, const float* v_posed, const flo
   static int force_generic = -1;
   if (force_generic < 0) { const char* e = getenv("HP3D_LBS"); force_generic = (e && !strcmp(e, "generic")) ? 1 : 0; }
   if (h->tile_nq_max > 0 && !force_generic) {
+    // HP3D_LBS_MODE (tuning sweeps): 0 = scalar FFMA, 2 meshes ahead; 1 = FFMA2, 2 ahead; 2 = FFMA2, 4 ahead;
+    // 3 = scalar FFMA, 4 ahead. Default: LBS_DEFAULT_MODE.
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("HP3D_LBS_MODE"); mode = (e && *e >= '0' && *e <= '3') ? (*e - '0') : LBS_DEFAULT_MODE; }
     const int grid = cdiv(M, LBS_G);
-    if (h->tile_nq_max <= 8)
-      lbs_tile_kernel<8><<<grid, 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M, h->tile_nq,
-          h->tile_joff, h->tile_w, h->tile_ustart, h->tile_uent, h->reg_rowptr, h->reg_slot, h->reg_val, h->pick_slot, h->tree,
-          vertices, joints);
-    else
-      lbs_tile_kernel<NQCAP><<<grid, 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M, h->tile_nq,
-          h->tile_joff, h->tile_w, h->tile_ustart, h->tile_uent, h->reg_rowptr, h->reg_slot, h->reg_val, h->pick_slot, h->tree,
-          vertices, joints);
+#define HP3D_LBS_LAUNCH(NQM, F2, PF)                                                                                   \
+    lbs_tile_kernel<NQM, F2, PF><<<grid, 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M, \
+        h->tile_nq, h->tile_joff, h->tile_w, h->tile_ustart, h->tile_uent, h->reg_rowptr, h->reg_slot, h->reg_val,      \
+        h->pick_slot, h->tree, vertices, joints)
+    if (h->tile_nq_max <= 8) {
+      switch (mode) {
+        case 0: HP3D_LBS_LAUNCH(8, false, 2); break;
+        case 1: HP3D_LBS_LAUNCH(8, true, 2); break;
+        case 2: HP3D_LBS_LAUNCH(8, true, 4); break;
+        default: HP3D_LBS_LAUNCH(8, false, 4); break;
+      }
+    } else {
+      if (mode == 1 || mode == 2) HP3D_LBS_LAUNCH(NQCAP, true, 2); else HP3D_LBS_LAUNCH(NQCAP, false, 2);
+    }
+#undef HP3D_LBS_LAUNCH
     return launch_status("lbs_tile_kernel");
   }
   const int grid = std::min(M, 148 * 8);
