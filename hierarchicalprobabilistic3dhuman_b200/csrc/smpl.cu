@@ -284,8 +284,8 @@ constexpr int TV = 64;                      // vertices per tile
 constexpr int NT = (NV + TV - 1) / TV;      // 108
 constexpr int NQCAP = 12;
 constexpr int LBS_G = 8;                    // meshes per CTA (== warps per CTA)
-constexpr int NU_MAX = NPICK + 255;
-constexpr int LBS_DEFAULT_MODE = 1;         // see hp3d_smpl_lbs         // unique vertices feeding the 66 extra joints (<= 276)
+constexpr int NU_MAX = NPICK + 255;         // unique vertices feeding the 66 extra joints (<= 276)
+constexpr int LBS_DEFAULT_MODE = 1;         // FFMA2 blending, 2 meshes ahead (see hp3d_smpl_lbs; profiles/r01i_lbs_sweep.jsonl)
 
 struct LbsTileCtx {
   int tile, lane, m0, Gv, park0, park1;
