@@ -15,6 +15,7 @@ EXPORTS = [
     "hp3d_vertex_uncertainty", "hp3d_rank_samples_by_joints2d", "hp3d_mf_sample",
     "hp3d_head_create", "hp3d_head_destroy", "hp3d_head_workspace_bytes", "hp3d_head_forward",
     "hp3d_encoder_create", "hp3d_encoder_destroy", "hp3d_encoder_workspace_bytes", "hp3d_encoder_forward", "hp3d_encoder_forward_taps",
+    "hp3d_encoder_forward_image", "hp3d_canny_edges", "hp3d_joints2d_to_heatmaps", "hp3d_proxy_rep", "hp3d_joints2d_heatmap_argmax",
 ]
 
 
@@ -85,6 +86,14 @@ def lib():
     L.hp3d_encoder_forward_taps.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]
     L.hp3d_rank_samples_by_joints2d.argtypes = [c_void_p, c_void_p, ctypes.c_longlong, c_void_p, c_int, c_int, c_int, c_int, c_float,
                                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    LL = ctypes.c_longlong
+    L.hp3d_canny_edges.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_float, c_int] + [c_void_p] * 7 + [LL, c_void_p]
+    L.hp3d_joints2d_to_heatmaps.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, LL, c_void_p]
+    L.hp3d_proxy_rep.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_float, c_int, c_float,
+                                 c_void_p, c_void_p]
+    L.hp3d_joints2d_heatmap_argmax.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p]
+    L.hp3d_encoder_forward_image.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_float, c_int,
+                                             c_float, c_void_p, c_void_p, c_size_t, c_void_p]
     _lib = L
     return L
 

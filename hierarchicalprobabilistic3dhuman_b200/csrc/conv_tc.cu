@@ -756,7 +756,7 @@ size_t encoder_tc_workspace_bytes(const void*, int B, int H, int W) {
 }
 
 int encoder_tc_forward(const void* p, const float* x, int B, int H, int W, float* feats, void* workspace,
-                       size_t workspace_bytes, float* taps, cudaStream_t s) {
+                       size_t workspace_bytes, float* taps, cudaStream_t s, const ImageInput* image) {
   const EncoderTc* E = (const EncoderTc*)p;
   if (H != 256 || W != 256) { set_error("HP3D_ENC_FAST supports 256x256 proxy representations (DATA.PROXY_REP_SIZE)"); return -1; }
   const int Bp = (B + 1) & ~1;
@@ -765,8 +765,14 @@ int encoder_tc_forward(const void* p, const float* x, int B, int H, int W, float
   __half* stem = (__half*)ws; ws += act_bytes(Bp, H / 2, W / 2, 64);
   __half* buf[4];
   for (int i = 0; i < 4; ++i) { buf[i] = (__half*)ws; ws += act_bytes(Bp, H / 4, W / 4, 64); }
-  nchw_f32_to_nhwc32_f16_kernel<<<dim3(cdiv(H * W, 128), B), 256, 0, s>>>(x, 18, H * W, xin);
-  int rc = launch_status("nchw_f32_to_nhwc32_f16_kernel");
+  int rc;
+  if (image) {    // Canny edges + joint heat-maps written straight into the stem's fp16 NHWC(32) records (proxy.cu)
+    rc = proxy_rep_nhwc32_f16(image->rgb, image->joints2d, image->visibility, B, H, image->gaussian_std, image->gaussian_size,
+                              image->threshold, image->nms, image->heat_std, xin, s);
+  } else {
+    nchw_f32_to_nhwc32_f16_kernel<<<dim3(cdiv(H * W, 128), B), 256, 0, s>>>(x, 18, H * W, xin);
+    rc = launch_status("nchw_f32_to_nhwc32_f16_kernel");
+  }
   if (rc) return rc;
   rc = run_tc_conv(E, E->stem, xin, B, H, W, nullptr, 1, stem, s);
   if (rc) return rc;

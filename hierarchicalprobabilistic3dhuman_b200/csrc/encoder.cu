@@ -282,6 +282,18 @@ extern "C" int hp3d_encoder_forward(const hp3d_encoder* h, const float* x, int B
   return hp3d_encoder_forward_taps(h, x, B, H, W, feats, workspace, workspace_bytes, nullptr, stream_);
 }
 
+extern "C" int hp3d_encoder_forward_image(const hp3d_encoder* h, const float* rgb, const float* joints2d,
+                                          const unsigned char* visibility, int B, int img_wh, float gaussian_std,
+                                          int gaussian_size, float threshold, int nms, float heat_std, float* feats,
+                                          void* workspace, size_t workspace_bytes, void* stream_) {
+  HP3D_ARG(h && rgb && joints2d && feats && workspace, "null argument");
+  HP3D_ARG(h->mode == HP3D_ENC_FAST, "fused image input needs HP3D_ENC_FAST (parity mode: hp3d_proxy_rep + hp3d_encoder_forward)");
+  HP3D_ARG(B > 0 && img_wh == 256, "256x256 proxy representations (DATA.PROXY_REP_SIZE)");
+  HP3D_ARG(workspace_bytes >= hp3d_encoder_workspace_bytes(h, B, img_wh, img_wh), "workspace too small");
+  const ImageInput im = {rgb, joints2d, visibility, gaussian_std, gaussian_size, threshold, nms, heat_std};
+  return encoder_tc_forward(h->tc, nullptr, B, img_wh, img_wh, feats, workspace, workspace_bytes, nullptr, (cudaStream_t)stream_, &im);
+}
+
 extern "C" int hp3d_encoder_forward_taps(const hp3d_encoder* h, const float* x, int B, int H, int W, float* feats,
                                          void* workspace, size_t workspace_bytes, float* taps, void* stream_) {
   HP3D_ARG(h && x && feats && workspace, "null argument");

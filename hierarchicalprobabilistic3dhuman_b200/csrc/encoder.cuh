@@ -7,8 +7,16 @@ int fold_conv_bn(const hp3d_conv_bn& c, float eps, int cin_pad, std::vector<floa
 int encoder_tc_create(const hp3d_encoder_weights* w, void** out);
 void encoder_tc_destroy(void* p);
 size_t encoder_tc_workspace_bytes(const void* p, int B, int H, int W);
+// image-space input of the fused proxy-representation producer (proxy.cu); when given, x_nchw is ignored
+struct ImageInput {
+  const float* rgb; const float* joints2d; const unsigned char* visibility;
+  float gaussian_std; int gaussian_size; float threshold; int nms; float heat_std;
+};
 int encoder_tc_forward(const void* p, const float* x_nchw, int B, int H, int W, float* feats, void* workspace,
-                       size_t workspace_bytes, float* taps, cudaStream_t stream);
+                       size_t workspace_bytes, float* taps, cudaStream_t stream, const ImageInput* image = nullptr);
+int proxy_rep_nhwc32_f16(const float* rgb, const float* joints2d, const unsigned char* visibility, int B, int img_wh,
+                         float gaussian_std, int gaussian_size, float threshold, int nms, float heat_std, void* nhwc32,
+                         cudaStream_t stream);
 // append `count` activation values (converted to fp32) to the debug tap buffer
 int tap_copy_f32(const float* src, size_t count, float** taps, cudaStream_t s);
 int tap_copy_f16(const void* src, size_t count, float** taps, cudaStream_t s);

@@ -93,12 +93,15 @@ __global__ void __launch_bounds__(256) rank_samples_kernel(const float* __restri
 extern "C" int hp3d_rank_samples_by_joints2d(const float* joints, const float* heatmaps, long long heatmap_image_stride,
                                              const float* cam, int B, int N, int H, int W, float eps, int32_t* order,
                                              float* err, float* joints2d_out, int32_t* vis_out, void* stream_) {
-  HP3D_ARG(joints && heatmaps && cam && order && err && joints2d_out && vis_out, "null argument");
+  HP3D_ARG(joints && cam && order && err && joints2d_out && vis_out, "null argument");
   HP3D_ARG(B > 0 && N > 0 && N <= 4096 && H > 0 && W > 0, "need B > 0, 0 < N <= 4096");
   cudaStream_t s = (cudaStream_t)stream_;
-  heatmap_argmax_kernel<<<dim3(17, B), 256, 0, s>>>(heatmaps, (size_t)heatmap_image_stride, H * W, W, eps, joints2d_out, vis_out);
-  int rc = launch_status("heatmap_argmax_kernel");
-  if (rc) return rc;
+  int rc = 0;
+  if (heatmaps) {     // else joints2d_out / vis_out already hold the input joints (hp3d_joints2d_heatmap_argmax)
+    heatmap_argmax_kernel<<<dim3(17, B), 256, 0, s>>>(heatmaps, (size_t)heatmap_image_stride, H * W, W, eps, joints2d_out, vis_out);
+    rc = launch_status("heatmap_argmax_kernel");
+    if (rc) return rc;
+  }
   int P = 1; while (P < N) P <<= 1;
   rank_samples_kernel<<<B, 256, (size_t)P * sizeof(unsigned long long), s>>>(joints, cam, joints2d_out, vis_out, N, W, order, err);
   return launch_status("rank_samples_kernel");

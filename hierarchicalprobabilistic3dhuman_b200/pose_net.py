@@ -169,6 +169,36 @@ class PoseMFShapeGaussianNet(nn.Module):
                                               _lib.stream_ptr()), "hp3d_encoder_forward")
         return feats
 
+    def encode_image(self, rgb, joints2D, visibility=None, threshold=0.0, non_max_suppression=True, gaussian_filter_std=1.0,
+                     gaussian_filter_size=5, heatmap_std=4.0):
+        """Image-space entry: (B,3,256,256) RGB crop in [0,1], (B,17,2) 2D joints, (B,17)
+        visibility -> (B,512) features, i.e. reference predict/...:91-100 (Canny edges, joint heat-maps, mask, cat)
+        followed by models/resnet.py:202-217. In fast mode one kernel writes the stem's fp16 NHWC input directly (the
+        fp32 proxy representation never exists); in parity mode it is materialised and fed to `encode`."""
+        from .proxy import proxy_representation, _vis_bytes
+        _lib.require_cuda(rgb, "rgb")
+        dev = rgb.device
+        if self.encoder_mode != "fast":
+            return self.encode(proxy_representation(rgb, joints2D, visibility, threshold, non_max_suppression,
+                                                    gaussian_filter_std, gaussian_filter_size, heatmap_std))
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        enc, _ = self._build_handles(key, True)
+        x = rgb.detach().to(torch.float32).contiguous()
+        j = _lib.require_cuda(joints2D, "joints2D").detach().to(torch.float32).contiguous()
+        B, C, H, W = x.shape
+        assert C == 3 and H == W and j.shape == (B, 17, 2)
+        vis = _vis_bytes(visibility, dev)
+        L = _lib.lib()
+        feats = torch.empty(B, 512, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            nbytes = L.hp3d_encoder_workspace_bytes(enc, B, H, W)
+            ws = self._ws.get(nbytes, dev)
+            _lib.check(L.hp3d_encoder_forward_image(enc, x.data_ptr(), j.data_ptr(), vis.data_ptr() if vis is not None else None,
+                                                    B, H, float(gaussian_filter_std), int(gaussian_filter_size), float(threshold),
+                                                    int(bool(non_max_suppression)), float(heatmap_std), feats.data_ptr(),
+                                                    ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "hp3d_encoder_forward_image")
+        return feats
+
     def encode_taps(self, input):
         """Debug/parity helper: (feats, [stem, pool, layer1.0, ..., layer4.1]) with every activation as an
         fp32 NHWC tensor (hp3d_encoder_forward_taps)."""

@@ -85,25 +85,33 @@ def compute_vertex_uncertainties_by_poseMF_shapeGaussian_sampling(pose_U, pose_S
     return dist[0], out.vertices, out.joints
 
 
-def rank_samples_by_joints2d(joints_samples, proxy_rep_or_heatmaps, cam_wp, eps=1e-6):
+def rank_samples_by_joints2d(joints_samples, proxy_rep_or_heatmaps, cam_wp, eps=1e-6, joints2d=None, img_wh=256, std=4.0):
     """Batched core of the reference's `joints2D_error_sorted_verts_sampling` (utils/sampling_utils.py:195-233):
     joints_samples (B,N,90,3), proxy representation (B,18,H,W) or heat-maps (B,17,H,W), cam_wp (B,3) ->
-    dict(order (B,N) int64 sample indices by ascending 2D-joint error, error (B,N), joints2d (B,17,2), vis (B,17))."""
+    dict(order (B,N) int64 sample indices by ascending 2D-joint error, error (B,N), joints2d (B,17,2), vis (B,17)).
+    Image-space path: pass `joints2d=(joints2D (B,17,2), visibility (B,17) or None)` and None for the heat-maps; their
+    arg-max is then computed without materialising them (hp3d_joints2d_heatmap_argmax)."""
     _lib.require_cuda(joints_samples, "joints_samples")
     dev = joints_samples.device
     J = joints_samples.detach().to(torch.float32).contiguous()
-    hm = proxy_rep_or_heatmaps.detach().to(device=dev, dtype=torch.float32).contiguous()
     B, N = J.shape[0], J.shape[1]
-    C, H, W = hm.shape[1], hm.shape[2], hm.shape[3]
-    assert C in (17, 18) and hm.shape[0] == B
-    first = hm[:, C - 17:]                                   # view: heat-maps start at channel C-17
     cam = cam_wp.detach().to(device=dev, dtype=torch.float32).contiguous()
     order = torch.empty(B, N, device=dev, dtype=torch.int32)
     err = torch.empty(B, N, device=dev, dtype=torch.float32)
-    j2d = torch.empty(B, 17, 2, device=dev, dtype=torch.float32)
-    vis = torch.empty(B, 17, device=dev, dtype=torch.int32)
+    if joints2d is not None:
+        from .proxy import joints2d_heatmap_argmax
+        j2d, vis = joints2d_heatmap_argmax(joints2d[0], joints2d[1], img_wh, std, eps)
+        assert j2d.shape == (B, 17, 2)
+        hm_ptr, stride, H, W = None, 0, img_wh, img_wh
+    else:
+        hm = proxy_rep_or_heatmaps.detach().to(device=dev, dtype=torch.float32).contiguous()
+        C, H, W = hm.shape[1], hm.shape[2], hm.shape[3]
+        assert C in (17, 18) and hm.shape[0] == B
+        hm_ptr, stride = hm[:, C - 17:].data_ptr(), C * H * W     # heat-maps start at channel C-17
+        j2d = torch.empty(B, 17, 2, device=dev, dtype=torch.float32)
+        vis = torch.empty(B, 17, device=dev, dtype=torch.int32)
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().hp3d_rank_samples_by_joints2d(J.data_ptr(), first.data_ptr(), C * H * W, cam.data_ptr(), B, N, H, W,
+        _lib.check(_lib.lib().hp3d_rank_samples_by_joints2d(J.data_ptr(), hm_ptr, stride, cam.data_ptr(), B, N, H, W,
                                                             float(eps), order.data_ptr(), err.data_ptr(), j2d.data_ptr(),
                                                             vis.data_ptr(), _lib.stream_ptr()), "hp3d_rank_samples_by_joints2d")
     return dict(order=order.long(), error=err, joints2d=j2d, vis=vis.bool())

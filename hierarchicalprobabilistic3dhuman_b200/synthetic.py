@@ -156,6 +156,32 @@ def synthetic_proxy_rep(batch, seed=0, size=256, std=4.0):
     return out
 
 
+def synthetic_images(batch, seed=0, size=256):
+    """Image-space inputs of the proxy-representation generator (reference predict/...:84-99): a (B,3,size,size)
+    float32 RGB crop in [0,1] (smooth random colour field + mild pixel noise, so Canny finds real edge structure),
+    (B,17,2) float32 2D joints as (u, v) -- a few of them outside the image --, and the (B,17) bool visibility mask
+    (joints {7,8,9,10,13,14,15,16} dropped w.p. 0.1, predict/...:97-98)."""
+    rs = np.random.RandomState(seed)
+    rgb = np.zeros((batch, 3, size, size), dtype=np.float32)
+    fy = np.linspace(0, 18.999, size)
+    y0 = fy.astype(int)
+    wy = (fy - y0).astype(np.float32)
+    for b in range(batch):
+        coarse = rs.uniform(0, 1, size=(3, 21, 21)).astype(np.float32)
+        f = ((1 - wy)[None, :, None] * (1 - wy)[None, None, :] * coarse[:, y0][:, :, y0]
+             + (1 - wy)[None, :, None] * wy[None, None, :] * coarse[:, y0][:, :, y0 + 1]
+             + wy[None, :, None] * (1 - wy)[None, None, :] * coarse[:, y0 + 1][:, :, y0]
+             + wy[None, :, None] * wy[None, None, :] * coarse[:, y0 + 1][:, :, y0 + 1])
+        f = f + rs.normal(0, 0.02, size=f.shape).astype(np.float32)
+        rgb[b] = np.clip(f, 0.0, 1.0)
+    j2d = rs.uniform(-8.0, size + 8.0, size=(batch, 17, 2)).astype(np.float32)
+    vis = np.ones((batch, 17), dtype=bool)
+    for b in range(batch):
+        for j in (7, 8, 9, 10, 13, 14, 15, 16):
+            vis[b, j] = rs.uniform() >= 0.1
+    return rgb, j2d, vis
+
+
 def randomise_bn_stats(module, seed=0):
     """running_mean~N(0,0.1), running_var~U(0.5,1.5), gamma~U(0.5,1.5), beta~N(0,0.1) on every
     BatchNorm2d of a torch module, from a numpy stream (torch-version independent)."""

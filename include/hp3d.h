@@ -78,10 +78,36 @@ int hp3d_vertex_uncertainty(const float* vertices, int B, int N, float* mean_ver
  * joints [B*N*90*3]; heatmaps = pointer to the FIRST of 17 joint heat-maps (H*W floats each) of image 0, consecutive
  * images `heatmap_image_stride` floats apart (for a (B,18,H,W) proxy representation: base + H*W, stride 18*H*W);
  * cam [B*3] weak-perspective (s,tx,ty). Outputs: order [B*N] sample indices by ascending error, err [B*N] (max pixel
- * distance over visible COCO joints), joints2d_out [B*17*2] heat-map arg-max (x,y; -1 if invisible), vis_out [B*17]. */
+ * distance over visible COCO joints), joints2d_out [B*17*2] heat-map arg-max (x,y; -1 if invisible), vis_out [B*17].
+ * heatmaps == NULL: joints2d_out / vis_out are INPUTS holding those arg-max joints already (image-space path:
+ * hp3d_joints2d_heatmap_argmax), and the heat-maps are never read. */
 int hp3d_rank_samples_by_joints2d(const float* joints, const float* heatmaps, long long heatmap_image_stride,
                                   const float* cam, int B, int N, int H, int W, float eps, int32_t* order, float* err,
                                   float* joints2d_out, int32_t* vis_out, void* stream);
+
+/* ---------------------------------------------------------------- proxy-representation generation
+ * replaces: models/canny_edge_detector.py:104-166 (CannyEdgeDetector.forward). img [B*C*H*W] fp32 NCHW; Gaussian
+ * taps = scipy.signal.windows.gaussian(size, std)/sum (size odd, <= 9); every optional output may be NULL:
+ * blurred [B*C*H*W]; grad_mag, grad_ori, thr_grad_mag, thin_edges, thr_thin_edges [B*H*W] (the reference's dict keys;
+ * the two thin_* need nms != 0); edges = what predict/...:92 feeds the network (thr_thin_edges if nms else
+ * thr_grad_mag), image b written at edges + b*edges_image_stride (e.g. channel 0 of a (B,18,H,W) tensor). */
+int hp3d_canny_edges(const float* img, int B, int C, int H, int W, float gaussian_std, int gaussian_size,
+                     float threshold, int nms, float* blurred, float* grad_mag, float* grad_ori, float* thr_grad_mag,
+                     float* thin_edges, float* thr_thin_edges, float* edges, long long edges_image_stride, void* stream);
+/* replaces: utils/label_conversions.py:105-124 (convert_2Djoints_to_gaussian_heatmaps_torch) and the visibility
+ * mask of predict/...:97-99. joints2d [B*K*2] as (u = column, v = row); visibility [B*K] bytes or NULL;
+ * heat-map k of image b written at out + b*out_image_stride + k*wh*wh. */
+int hp3d_joints2d_to_heatmaps(const float* joints2d, const unsigned char* visibility, int B, int K, int img_wh,
+                              float std, float* out, long long out_image_stride, void* stream);
+/* replaces: predict/...:91-100 in one launch: out_nchw [B*(K+1)*wh*wh] = cat(edges, masked heat-maps). K <= 32. */
+int hp3d_proxy_rep(const float* rgb, const float* joints2d, const unsigned char* visibility, int B, int C, int K,
+                   int img_wh, float gaussian_std, int gaussian_size, float threshold, int nms, float heat_std,
+                   float* out_nchw, void* stream);
+/* arg-max pixel and visibility (max > eps) of each joint's heat-map WITHOUT materialising it: what
+ * utils/label_conversions.py:127-155 returns for the maps of hp3d_joints2d_to_heatmaps. joints2d_px [B*K*2]
+ * (x, y; -1 if invisible), vis_out [B*K]. */
+int hp3d_joints2d_heatmap_argmax(const float* joints2d, const unsigned char* visibility, int B, int K, int img_wh,
+                                 float std, float eps, float* joints2d_px, int32_t* vis_out, void* stream);
 
 /* ---------------------------------------------------------------- matrix-Fisher sampler
  * replaces: utils/sampling_utils.py:74-143 (pose_matrix_fisher_sampling_torch) incl. :10-71
@@ -143,6 +169,13 @@ size_t hp3d_encoder_workspace_bytes(const hp3d_encoder* h, int B, int H, int W);
 /* x [B*18*H*W] fp32 NCHW (the reference's input layout, predict/...:100) -> feats [B*512] */
 int hp3d_encoder_forward(const hp3d_encoder* h, const float* x_nchw, int B, int H, int W, float* feats,
                          void* workspace, size_t workspace_bytes, void* stream);
+/* image-space entry (HP3D_ENC_FAST handles only): rgb [B*3*256*256] in [0,1], joints2d [B*17*2], visibility [B*17]
+ * bytes or NULL -> feats. The Canny + heat-map kernel writes the stem's fp16 NHWC input records directly: the fp32
+ * proxy representation of predict/...:100 never exists in memory. Same workspace as hp3d_encoder_forward. */
+int hp3d_encoder_forward_image(const hp3d_encoder* h, const float* rgb, const float* joints2d,
+                               const unsigned char* visibility, int B, int img_wh, float gaussian_std, int gaussian_size,
+                               float threshold, int nms, float heat_std, float* feats, void* workspace,
+                               size_t workspace_bytes, void* stream);
 /* same, additionally dumping every post-activation tensor as fp32 NHWC into `taps` in the order
  * stem (B,H/2,W/2,64) | maxpool (B,H/4,W/4,64) | layer1.0 | layer1.1 | ... | layer4.1  (parity debugging of the
  * per-layer kernels against models/resnet.py:203-212; taps == NULL behaves like hp3d_encoder_forward). */

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-from oracle import reference_import, net_oracle, sampler_oracle   # noqa: E402
+from oracle import reference_import, net_oracle, sampler_oracle, proxy_oracle   # noqa: E402
 from hierarchicalprobabilistic3dhuman_b200 import synthetic as syn   # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
@@ -79,6 +79,57 @@ def main():
         assert torch.equal(R, R2), name
         np.savez_compressed(os.path.join(GOLD, name + ".npz"), R=R.numpy(), U=Un, S=Sn, V=Vn, N=N, seed=seed,
                             accepted=acc.numpy(), noise_checksum=checksum(eps) + checksum(w))
+    # ---- sample-ranking helpers: heat-map arg-max and projection, the reference's own functions
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        from utils.label_conversions import (convert_heatmaps_to_2Djoints_coordinates_torch,
+                                             convert_2Djoints_to_gaussian_heatmaps_torch)
+        from utils.cam_utils import orthographic_project_torch
+        from utils.joints2d_utils import undo_keypoint_normalisation
+        from models.canny_edge_detector import CannyEdgeDetector
+    xr = torch.from_numpy(syn.synthetic_proxy_rep(3, seed=5))
+    j2d_r, vis_r = convert_heatmaps_to_2Djoints_coordinates_torch(xr[:, 1:], eps=1e-6)
+    j2d_o, vis_o = sampler_oracle.heatmaps_to_joints2d(xr[:, 1:])
+    assert torch.equal(j2d_r, j2d_o) and torch.equal(vis_r, vis_o)
+    rs = np.random.RandomState(3)
+    Jc = torch.from_numpy(rs.normal(0, 0.4, size=(5, 17, 3)).astype(np.float32))
+    camr = torch.tensor([[0.87, 0.05, -0.1]])
+    flipped = Jc * torch.tensor([1.0, -1.0, -1.0])      # pytorch3d 180-degree flip about x is absent here: restated
+    px_r = undo_keypoint_normalisation(orthographic_project_torch(flipped, camr), 256)
+    px_o = sampler_oracle.project_joints_to_pixels(Jc, camr, 256)
+    assert torch.equal(px_r, px_o)
+    np.savez_compressed(os.path.join(GOLD, "rank_helpers.npz"), joints2d=j2d_r.numpy(), vis=vis_r.numpy(), J=Jc.numpy(),
+                        cam=camr.numpy(), pixels=px_r.numpy(), proxy_seed=5)
+
+    # ---- proxy-representation generation: the reference's CannyEdgeDetector and heat-maps
+    rgb, j2d, vis = (torch.from_numpy(a) for a in syn.synthetic_images(2, seed=5))
+    store = {"image_seed": 5, "rgb_checksum": checksum(rgb), "joints2d": j2d.numpy(), "vis": vis.numpy()}
+    for tag, thr, nms in (("cfg", 0.0, True), ("thr", 0.2, True), ("nonms", 0.1, False)):   # cfg = configs/...:21-24
+        det = CannyEdgeDetector(non_max_suppression=nms, gaussian_filter_std=1.0, gaussian_filter_size=5, threshold=thr)
+        with torch.no_grad():
+            r_ = det(rgb)
+        o_ = proxy_oracle.canny_edges(rgb, thr, nms)
+        for k in r_:
+            assert torch.equal(r_[k], o_[k]), (tag, k)             # restatement is bit-identical to the reference
+        key = "thresholded_thin_edges" if nms else "thresholded_grad_magnitude"
+        store[f"edges_{tag}"] = r_[key].numpy()
+        if tag == "cfg":
+            store["grad_orientation"] = r_["grad_orientation"].numpy().astype(np.uint16)   # multiples of 45 <= 360
+            store["blurred_checksum"] = checksum(r_["blurred_img"])
+            store["grad_magnitude_checksum"] = checksum(r_["grad_magnitude"])
+    heat_r = convert_2Djoints_to_gaussian_heatmaps_torch(j2d, 256, std=4)
+    assert torch.equal(heat_r, proxy_oracle.joints2d_to_heatmaps(j2d, 256, 4))
+    heat_m = heat_r * vis[:, :, None, None]
+    store["heat_checksum"] = checksum(heat_m)
+    store["heat_rows"] = heat_m[:, :, ::37, :].numpy()           # every 37th row of every map (7 rows): small, exact
+    jj, vv = convert_heatmaps_to_2Djoints_coordinates_torch(heat_m, eps=1e-6)
+    store["heat_argmax"], store["heat_argmax_vis"] = jj.numpy(), vv.numpy()
+    # the full network on this image-space input (reference predict/...:91-104)
+    proxy = torch.cat([torch.from_numpy(store["edges_cfg"]), heat_m], dim=1).float()
+    assert torch.equal(proxy, proxy_oracle.proxy_representation(rgb, j2d, vis))
+    with torch.no_grad():
+        store["feats"] = model.image_encoder(proxy).numpy()
+    np.savez_compressed(os.path.join(GOLD, "proxy_b2.npz"), **store)
     print("golden fixtures written to", os.path.normpath(GOLD))
     for f in sorted(os.listdir(GOLD)):
         print(" ", f, os.path.getsize(os.path.join(GOLD, f)))

@@ -82,3 +82,45 @@ def test_sample_ranking_helpers_match_reference_golden():
     order, err = sampler_oracle.rank_samples(joints, x[:, 1:], cam)
     assert all(sorted(o.tolist()) == list(range(11)) for o in order)
     assert (torch.gather(err, 1, order).diff(dim=1) >= 0).all()
+
+
+def test_proxy_representation_oracle_matches_reference_golden():
+    """Canny edges + joint heat-maps vs outputs of the reference's own CannyEdgeDetector /
+    convert_2Djoints_to_gaussian_heatmaps_torch: the restatement is bit-identical."""
+    from oracle import proxy_oracle
+    g = load_golden("proxy_b2")
+    rgb, j2d, vis = (torch.from_numpy(a) for a in syn.synthetic_images(2, seed=int(g["image_seed"])))
+    np.testing.assert_allclose(_checksum(rgb), g["rgb_checksum"], rtol=1e-12)
+    assert np.array_equal(j2d.numpy(), g["joints2d"]) and np.array_equal(vis.numpy(), g["vis"])
+    for tag, thr, nms in (("cfg", 0.0, True), ("thr", 0.2, True), ("nonms", 0.1, False)):
+        o = proxy_oracle.canny_edges(rgb, thr, nms)
+        key = "thresholded_thin_edges" if nms else "thresholded_grad_magnitude"
+        assert np.array_equal(o[key].numpy(), g[f"edges_{tag}"]), tag
+        if tag == "cfg":
+            assert np.array_equal(o["grad_orientation"].numpy().astype(np.uint16), g["grad_orientation"])
+            np.testing.assert_allclose(_checksum(o["blurred_img"]), g["blurred_checksum"], rtol=1e-12)
+            np.testing.assert_allclose(_checksum(o["grad_magnitude"]), g["grad_magnitude_checksum"], rtol=1e-12)
+    heat = proxy_oracle.joints2d_to_heatmaps(j2d, 256, 4, vis)
+    assert np.array_equal(heat[:, :, ::37, :].numpy(), g["heat_rows"])
+    np.testing.assert_allclose(_checksum(heat), g["heat_checksum"], rtol=1e-12)
+    jj, vv = sampler_oracle.heatmaps_to_joints2d(heat)
+    assert np.array_equal(jj.numpy(), g["heat_argmax"]) and np.array_equal(vv.numpy(), g["heat_argmax_vis"])
+    # edge maps are sparse, thin and non-negative; border pixels carry the zero-padding gradient
+    e = torch.from_numpy(g["edges_cfg"])
+    assert (e >= 0).all() and 0.05 < (e > 0).float().mean() < 0.5
+
+
+def test_proxy_oracle_small_known_answers():
+    from oracle import proxy_oracle
+    # a constant image has zero gradient away from the (zero-padded) border: no interior edges
+    e = proxy_oracle.canny_edges(torch.full((1, 3, 32, 32), 0.5), 0.0, True)
+    assert e["thresholded_thin_edges"][0, 0, 6:-6, 6:-6].abs().max() == 0
+    # a vertical step edge survives thinning as a 1-pixel-wide line with orientation 0/180 degrees
+    img = torch.zeros(1, 1, 32, 32); img[..., 16:] = 1.0
+    e = proxy_oracle.canny_edges(img, 0.0, True)
+    row = e["thresholded_thin_edges"][0, 0, 16]
+    assert (row[8:24] > 0).sum() == 1
+    assert set(e["grad_orientation"][0, 0, 16, 14:18].tolist()) <= {0.0, 180.0, 360.0}
+    # heat-map: peak 1 at an integer joint, (u, v) = (column, row)
+    h = proxy_oracle.joints2d_to_heatmaps(torch.tensor([[[5.0, 9.0]]]), 16, 4)
+    assert h[0, 0, 9, 5] == 1.0 and h[0, 0].argmax().item() == 9 * 16 + 5
