@@ -389,6 +389,164 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
   if (warp == 2) { tc_fence_after_sync(); tmem_dealloc<2 * BN>(tmem_base); }
 }
 
+// ---------------------------------------------------------------- stem, two M-tiles per weight pass
+// Timing experiments on the generic patch kernel (profiles/README.md, r01l) showed the 7x7/2 stem is bound by the
+// round-trip latency of its weight ring, not by bytes or MMAs: 224 KB of weights (28 taps x 8 KB) cannot stay resident
+// next to the patches, so every 128-pixel tile streams all of them through a 96 KB ring that covers only ~2300 cycles
+// of tensor work. This variant makes one weight stage (the 4 pair-taps of one filter row) feed TWO vertically adjacent
+// M-tiles (an 8 x 32 output block, two 64-column TMEM accumulators): weight traffic, barrier round trips and commits
+// per output halve, and a ring stage covers twice the MMA time. To keep the patch ring double-buffered in the same
+// shared-memory budget, a patch stage holds ONE row parity of the block (35 or 34 rows x 12 pixel-pair records), and
+// the filter rows are visited parity-major: kh = 0,2,4,6 (odd input rows), then kh = 1,3,5 (even input rows).
+constexpr int STEM2_PW = 12;                                         // patch pitch in 128-byte pixel-pair records
+constexpr int STEM2_STAGE_BYTES = (35 * STEM2_PW * 128 + 1023) / 1024 * 1024;   // 54,272
+constexpr int STEM2_PS = 2, STEM2_BS = 3, STEM2_TPS = 4;
+struct Stem2Smem {
+  static constexpr int B_BYTES = 64 * BLOCK_K * 2;                   // one tap: 8 KB
+  static constexpr int BSTAGE_BYTES = STEM2_TPS * B_BYTES;           // one filter row: 32 KB
+  static constexpr int B_OFFSET = STEM2_PS * STEM2_STAGE_BYTES;
+  static constexpr int BAR_OFFSET = B_OFFSET + STEM2_BS * BSTAGE_BYTES;
+  static constexpr int BIAS_OFFSET = BAR_OFFSET + 512;
+  static constexpr int TOTAL = BIAS_OFFSET + 64 * 4 + 1024;
+};
+struct Stem2Args {
+  int num_blocks, tiles_x, tiles_y;      // 8 x 32 output blocks
+  int Ho, Wo;
+  const float* bias;
+  __half* out;
+  int relu, debug;
+};
+
+__global__ void __launch_bounds__(256, 1)
+stem2_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1,
+             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ Stem2Args args) {
+  using L = Stem2Smem;
+  constexpr int BN = 64, PS = STEM2_PS, BS = STEM2_BS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* pfull = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* pempty = pfull + PS;
+  uint64_t* bfull = pempty + PS;
+  uint64_t* bempty = bfull + BS;
+  uint64_t* tmem_full = bempty + BS;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;   // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(smem + L::BIAS_OFFSET);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmP0); tma_prefetch_desc(&tmP1); tma_prefetch_desc(&tmB); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < PS; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 1); }
+    for (int s = 0; s < BS; ++s) { mbar_init(&bfull[s], 1); mbar_init(&bempty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<4 * BN>(tmem_base_slot);     // 2 accumulator sets x 2 tiles x 64 columns
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_base_slot;
+  // half 0: row parity 1 (kh = 0,2,4,6 -> dy = -2..1, 35 patch rows from oy0-2); half 1: parity 0 (kh = 1,3,5 -> dy = -1..1,
+  // 34 rows from oy0-1)
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    int ps = 0, bs = 0; uint32_t pphase = 0, bphase = 0;
+    for (int blk = blockIdx.x; blk < args.num_blocks; blk += gridDim.x) {
+      const int tx = blk % args.tiles_x, ty = (blk / args.tiles_x) % args.tiles_y;
+      const int n = blk / (args.tiles_x * args.tiles_y);
+      const int ox0 = tx * 8, oy0 = ty * 32;
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(&pempty[ps], pphase ^ 1, 21);
+        uint8_t* stage = smem + ps * STEM2_STAGE_BYTES;
+        if (args.debug & 4) { if (elect_one()) mbar_arrive(&pfull[ps]); }
+        else {
+          if (elect_one()) mbar_arrive_expect_tx(&pfull[ps], (half == 0 ? 35 : 34) * STEM2_PW * 128);
+          if (elect_one()) tma_load_4d(stage, half == 0 ? &tmP1 : &tmP0, &pfull[ps], 0, ox0 - 2, oy0 + (half == 0 ? -2 : -1), n);
+        }
+        if (++ps == PS) { ps = 0; pphase ^= 1; }
+        const int nrows = half == 0 ? 4 : 3;
+        for (int i = 0; i < nrows; ++i) {
+          const int kh = 2 * i + half;
+          mbar_wait(&bempty[bs], bphase ^ 1, 22);
+          if (args.debug & 4) { if (elect_one()) mbar_arrive(&bfull[bs]); }
+          else {
+            if (elect_one()) mbar_arrive_expect_tx(&bfull[bs], L::BSTAGE_BYTES);
+            if (elect_one()) tma_load_3d(smem + L::B_OFFSET + bs * L::BSTAGE_BYTES, &tmB, &bfull[bs], 0, 0, kh * 4);
+          }
+          if (++bs == BS) { bs = 0; bphase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    constexpr uint32_t idesc = umma_idesc_f16(BN);
+    int ps = 0, bs = 0; uint32_t pphase = 0, bphase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    const uint32_t b_base = smem_u32(smem + L::B_OFFSET);
+    for (int blk = blockIdx.x; blk < args.num_blocks; blk += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 23);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * BN);
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(&pfull[ps], pphase, 24);
+        tc_fence_after_sync();
+        const uint32_t stage = smem_u32(smem + ps * STEM2_STAGE_BYTES);
+        const int nrows = half == 0 ? 4 : 3;
+        for (int i = 0; i < nrows; ++i) {            // patch row offset of filter row kh = 2i + half is i (dy - p_oy)
+          mbar_wait(&bfull[bs], bphase, 25);
+          tc_fence_after_sync();
+          const uint32_t b_stage = b_base + (uint32_t)(bs * L::BSTAGE_BYTES);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+#pragma unroll
+            for (int dp = 0; dp < 4; ++dp) {
+              const uint32_t a_view = stage + (uint32_t)(((i + 16 * u) * STEM2_PW + dp) * 128);
+              const uint64_t a_desc = umma_desc_sw128_sbo(a_view, STEM2_PW * 128u);
+              const uint64_t b_desc = umma_desc_sw128(b_stage + (uint32_t)(dp * L::B_BYTES));
+              if (!(args.debug & 2)) {
+                if (elect_one()) umma_f16_x4(d_tmem + (uint32_t)(u * BN), a_desc, b_desc, idesc, (half | i | dp) != 0 ? 1u : 0u);
+              }
+            }
+          }
+          if (elect_one()) umma_commit(&bempty[bs]);
+          if (++bs == BS) { bs = 0; bphase ^= 1; }
+        }
+        if (elect_one()) umma_commit(&pempty[ps]);
+        if (++ps == PS) { ps = 0; pphase ^= 1; }
+      }
+      if (elect_one()) umma_commit(&tmem_full[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================================================== epilogue: two 128 x 64 accumulators per block
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    const int et = threadIdx.x - 128;
+    int acc = 0; uint32_t acc_phase = 0;
+    if (et < BN) bias_s[et] = args.bias[et];
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int yl = row >> 3, xl = row & 7;
+    for (int blk = blockIdx.x; blk < args.num_blocks; blk += gridDim.x) {
+      const int tx = blk % args.tiles_x, ty = (blk / args.tiles_x) % args.tiles_y;
+      const int n = blk / (args.tiles_x * args.tiles_y);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const size_t pix = ((size_t)n * args.Ho + (ty * 32 + u * 16 + yl)) * args.Wo + (tx * 8 + xl);
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * 2 * BN + u * BN);
+        conv_epilogue_tile<BN>(taddr, bias_s, nullptr, args.out, pix * BN, !(args.debug & 1), args.relu, &tmem_full[acc], acc_phase);
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after_sync(); tmem_dealloc<4 * BN>(tmem_base); }
+}
+
 // ---------------------------------------------------------------- elementwise helpers (fp16 NHWC)
 __global__ void __launch_bounds__(256) nchw_f32_to_nhwc32_f16_kernel(const float* __restrict__ x, int C, int HW,
                                                                      __half* __restrict__ y) {
@@ -685,6 +843,29 @@ int run_patch_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N,
   }
   const int grid = std::min(a.tiles_m * a.tiles_n, E->num_sms);
   CUtensorMap tmBg;     // weights grouped: TPS k-blocks (taps) per box
+  static int stem2 = -1;
+  if (stem2 < 0) { const char* e = getenv("HP3D_STEM2"); stem2 = (e && !strcmp(e, "0")) ? 0 : 1; }
+  if (L.stem && stem2 && Ho % 32 == 0 && L.cout == 64) {
+    // two M-tiles per weight pass (stem2_kernel): one row-parity patch of an 8 x 32 output block per stage
+    Stem2Args sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.tiles_x = Wo / 8; sa.tiles_y = Ho / 32; sa.num_blocks = sa.tiles_x * sa.tiles_y * N;
+    sa.Ho = Ho; sa.Wo = Wo; sa.bias = L.bias; sa.out = out; sa.relu = relu; sa.debug = a.debug;
+    CUtensorMap tp[2];
+    for (int ph = 0; ph < 2; ++ph) {
+      const uint64_t dims[4] = {64, (uint64_t)W / 2, (uint64_t)H / 2, Np};
+      const uint64_t st[3] = {128, (uint64_t)2 * W * 64, (uint64_t)H * W * 64};
+      const uint32_t box[4] = {64, STEM2_PW, (uint32_t)(ph == 0 ? 34 : 35), 1};
+      int rc = make_tmap_f16(&tp[ph], in + (size_t)ph * W * 32, 4, dims, st, box, true);
+      if (rc) return rc;
+    }
+    int rc = make_weight_tmap(L, STEM2_TPS, &tmBg); if (rc) return rc;
+    static_assert(Stem2Smem::TOTAL <= 232448, "shared memory budget");
+    static bool set2 = false;
+    if (!set2) { HP3D_CUDA(cudaFuncSetAttribute(stem2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Stem2Smem::TOTAL)); set2 = true; }
+    stem2_kernel<<<std::min(sa.num_blocks, E->num_sms), 256, Stem2Smem::TOTAL, s>>>(tp[0], tp[1], tmBg, sa);
+    return launch_status("stem2_kernel");
+  }
   if (L.stem) {
     int rc = make_weight_tmap(L, 4, &tmBg); if (rc) return rc;
     return launch_patch<64, false, 2, 3, STEM_PATCH_BYTES, 1, 4>(tmP[0], tmP[1], tmBg, a, grid, s);
