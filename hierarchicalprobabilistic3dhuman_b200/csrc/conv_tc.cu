@@ -250,7 +250,11 @@ struct PatchSmem {
   static constexpr int TOTAL = BIAS_OFFSET + 512 * 4 + 1024;
 };
 
-template <int BN, bool RESIDENT, int PS, int BS, int PATCH_STAGE_BYTES, int NKB_RES, int TPS>
+// FIXED3: the 3x3/1 geometry (9 taps, one patch of pitch PATCH3_PW) is baked in at compile time, so the MMA issuer's tap
+// loop is fully unrolled with immediate view offsets instead of reading the tap table per iteration (the unrolled stem
+// kernel below issues an MMA every ~60 cycles, this loop needed ~100).
+constexpr int PATCH3_PW = 16;
+template <int BN, bool RESIDENT, int PS, int BS, int PATCH_STAGE_BYTES, int NKB_RES, int TPS, bool FIXED3>
 __global__ void __launch_bounds__(256, 1)
 conv_patch_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ PatchArgs args) {
@@ -338,21 +342,40 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
           mbar_wait(&pfull[ps], pphase, 14);
           tc_fence_after_sync();
           const uint32_t stage = smem_u32(smem + ps * PATCH_STAGE_BYTES);
-          for (int t = 0; t < args.n_taps; ++t) {
-            uint32_t b_addr;
-            if (RESIDENT) b_addr = b_base + (uint32_t)((cb * args.n_taps + t) * L::B_BYTES);
-            else {
-              if (t % TPS == 0) { mbar_wait(&bfull[bs], bphase, 15); tc_fence_after_sync(); }
-              b_addr = b_base + (uint32_t)(bs * L::BSTAGE_BYTES + (t % TPS) * L::B_BYTES);
+          if constexpr (FIXED3) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              uint32_t b_addr;
+              if (RESIDENT) b_addr = b_base + (uint32_t)((cb * 9 + t) * L::B_BYTES);
+              else {
+                if (t % TPS == 0) { mbar_wait(&bfull[bs], bphase, 15); tc_fence_after_sync(); }
+                b_addr = b_base + (uint32_t)(bs * L::BSTAGE_BYTES + (t % TPS) * L::B_BYTES);
+              }
+              const uint32_t a_view = stage + (uint32_t)(((t / 3) * PATCH3_PW + (t % 3)) * 128);
+              const uint64_t a_desc = umma_desc_sw128_sbo(a_view, PATCH3_PW * 128u);
+              const uint64_t b_desc = umma_desc_sw128(b_addr);
+              if (!(args.debug & 2)) {
+                if (elect_one()) umma_f16_x4(d_tmem, a_desc, b_desc, idesc, (cb | t) != 0 ? 1u : 0u);
+              }
+              if (!RESIDENT && (t % TPS) == TPS - 1) { if (elect_one()) umma_commit(&bempty[bs]); if (++bs == BS) { bs = 0; bphase ^= 1; } }
             }
-            const int p = args.t_patch[t];
-            const uint32_t a_view = stage + (uint32_t)args.p_base[p] + (uint32_t)args.t_off[t] * 128u;
-            const uint64_t a_desc = umma_desc_sw128_sbo(a_view, (uint32_t)args.p_pw[p] * 128u);   // 8-row groups are one patch row apart
-            const uint64_t b_desc = umma_desc_sw128(b_addr);
-            if (!(args.debug & 2)) {
-              if (elect_one()) umma_f16_x4(d_tmem, a_desc, b_desc, idesc, (cb | t) != 0 ? 1u : 0u);
+          } else {
+            for (int t = 0; t < args.n_taps; ++t) {
+              uint32_t b_addr;
+              if (RESIDENT) b_addr = b_base + (uint32_t)((cb * args.n_taps + t) * L::B_BYTES);
+              else {
+                if (t % TPS == 0) { mbar_wait(&bfull[bs], bphase, 15); tc_fence_after_sync(); }
+                b_addr = b_base + (uint32_t)(bs * L::BSTAGE_BYTES + (t % TPS) * L::B_BYTES);
+              }
+              const int p = args.t_patch[t];
+              const uint32_t a_view = stage + (uint32_t)args.p_base[p] + (uint32_t)args.t_off[t] * 128u;
+              const uint64_t a_desc = umma_desc_sw128_sbo(a_view, (uint32_t)args.p_pw[p] * 128u);   // 8-row groups are one patch row apart
+              const uint64_t b_desc = umma_desc_sw128(b_addr);
+              if (!(args.debug & 2)) {
+                if (elect_one()) umma_f16_x4(d_tmem, a_desc, b_desc, idesc, (cb | t) != 0 ? 1u : 0u);
+              }
+              if (!RESIDENT && (t % TPS) == TPS - 1) { if (elect_one()) umma_commit(&bempty[bs]); if (++bs == BS) { bs = 0; bphase ^= 1; } }
             }
-            if (!RESIDENT && (t % TPS) == TPS - 1) { if (elect_one()) umma_commit(&bempty[bs]); if (++bs == BS) { bs = 0; bphase ^= 1; } }
           }
           if (elect_one()) umma_commit(&pempty[ps]);
           if (++ps == PS) { ps = 0; pphase ^= 1; }
@@ -777,17 +800,17 @@ int run_tc_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N, in
 
 // Patch-variant launch. Returns PATCH_NOT_COVERED if this layer/geometry is not handled (caller falls back to conv_tc_kernel).
 constexpr int PATCH_NOT_COVERED = -1000;
-template <int BN, bool RESIDENT, int PS, int BS, int PSB, int NKB, int TPS>
+template <int BN, bool RESIDENT, int PS, int BS, int PSB, int NKB, int TPS, bool FIXED3>
 int launch_patch(const CUtensorMap& p0, const CUtensorMap& p1, const CUtensorMap& b, const PatchArgs& a, int grid, cudaStream_t s) {
   using SL = PatchSmem<BN, RESIDENT, PS, BS, PSB, NKB, TPS>;
   static_assert(SL::TOTAL <= 232448, "shared memory budget");
   static bool set = false;
-  if (!set) { HP3D_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, RESIDENT, PS, BS, PSB, NKB, TPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL)); set = true; }
-  conv_patch_kernel<BN, RESIDENT, PS, BS, PSB, NKB, TPS><<<grid, 256, SL::TOTAL, s>>>(p0, p1, b, a);
+  if (!set) { HP3D_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, RESIDENT, PS, BS, PSB, NKB, TPS, FIXED3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL)); set = true; }
+  conv_patch_kernel<BN, RESIDENT, PS, BS, PSB, NKB, TPS, FIXED3><<<grid, 256, SL::TOTAL, s>>>(p0, p1, b, a);
   return launch_status("conv_patch_kernel");
 }
 
-constexpr int PATCH_PW = 16;                                          // patch pitch in pixels (8 outputs + halo, padded)
+constexpr int PATCH_PW = PATCH3_PW;                                   // patch pitch in pixels (8 outputs + halo, padded)
 constexpr int PATCH3_BYTES = 18 * PATCH_PW * 128;                     // 3x3/1 halo patch of an 8x16 tile, 64 channels: 36 KB
 constexpr int STEM_PW = 12;                                           // stem patch pitch: 8 outputs + 3 halo pairs, padded to 12
 constexpr int STEM_PATCH_TX = (18 + 19) * STEM_PW * 128;              // two row-parity patches of pixel pairs: 55.5 KB
@@ -868,15 +891,15 @@ int run_patch_conv(const EncoderTc* E, const TcConv& L, const __half* in, int N,
   }
   if (L.stem) {
     int rc = make_weight_tmap(L, 4, &tmBg); if (rc) return rc;
-    return launch_patch<64, false, 2, 3, STEM_PATCH_BYTES, 1, 4>(tmP[0], tmP[1], tmBg, a, grid, s);
+    return launch_patch<64, false, 2, 3, STEM_PATCH_BYTES, 1, 4, false>(tmP[0], tmP[1], tmBg, a, grid, s);
   }
   if (L.bn == 64 && a.n_cblk == 1) {
     int rc = make_weight_tmap(L, 9, &tmBg); if (rc) return rc;
-    return launch_patch<64, true, 3, 1, PATCH3_BYTES, 9, 1>(tmP[0], tmP[1], tmBg, a, grid, s);
+    return launch_patch<64, true, 3, 1, PATCH3_BYTES, 9, 1, true>(tmP[0], tmP[1], tmBg, a, grid, s);
   }
   if (L.bn == 128) {
     int rc = make_weight_tmap(L, 3, &tmBg); if (rc) return rc;
-    return launch_patch<128, false, 3, 2, PATCH3_BYTES, 1, 3>(tmP[0], tmP[1], tmBg, a, grid, s);
+    return launch_patch<128, false, 3, 2, PATCH3_BYTES, 1, 3, true>(tmP[0], tmP[1], tmBg, a, grid, s);
   }
   return PATCH_NOT_COVERED;
 }
