@@ -571,26 +571,60 @@ stem2_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ C
 }
 
 // ---------------------------------------------------------------- elementwise helpers (fp16 NHWC)
+// ARGMAX: additionally track, per image and heat-map channel 1..17, the first maximum above `eps` as a packed key
+// (float bits << 32 | ~pixel index; atomicMax keeps the largest value and, on ties, the lowest index = torch.max's
+// arg-max): the sample-ranking step (utils/label_conversions.py:127-155) then never re-reads the 1.1 GB of heat-maps.
+template <bool ARGMAX>
 __global__ void __launch_bounds__(256) nchw_f32_to_nhwc32_f16_kernel(const float* __restrict__ x, int C, int HW,
-                                                                     __half* __restrict__ y) {
+                                                                     __half* __restrict__ y, float eps,
+                                                                     unsigned long long* __restrict__ keys) {
   // thread = (pixel, 16-channel half): 16 (or C-16) coalesced plane reads -> one full 32-byte sector of the
   // NHWC record (two 16-byte stores); channels >= C are written as zero padding.
+  __shared__ unsigned long long skey[32];
   const int n = blockIdx.y;
   const int p = blockIdx.x * 128 + (threadIdx.x & 127);
   const int half_id = threadIdx.x >> 7;               // 0: channels 0..15, 1: channels 16..31
-  if (p >= HW) return;
-  const float* src = x + (size_t)n * C * HW + p;
-  __half2 h[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int c0 = half_id * 16 + 2 * k;
-    const float a = (c0 < C) ? src[(size_t)c0 * HW] : 0.f;
-    const float b = (c0 + 1 < C) ? src[(size_t)(c0 + 1) * HW] : 0.f;
-    h[k] = __floats2half2_rn(a, b);
+  if (ARGMAX) {
+    if (threadIdx.x < 32) skey[threadIdx.x] = 0ull;
+    __syncthreads();
   }
-  uint4* dst = reinterpret_cast<uint4*>(y + ((size_t)n * HW + p) * 32 + half_id * 16);
-  dst[0] = *reinterpret_cast<const uint4*>(&h[0]);
-  dst[1] = *reinterpret_cast<const uint4*>(&h[4]);
+  if (p < HW) {
+    const float* src = x + (size_t)n * C * HW + p;
+    __half2 h[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c0 = half_id * 16 + 2 * k;
+      const float a = (c0 < C) ? src[(size_t)c0 * HW] : 0.f;
+      const float b = (c0 + 1 < C) ? src[(size_t)(c0 + 1) * HW] : 0.f;
+      h[k] = __floats2half2_rn(a, b);
+      if (ARGMAX) {
+        const unsigned long long lo = (unsigned long long)(0xFFFFFFFFu - (unsigned)p);
+        if (c0 >= 1 && c0 < C && a > eps) atomicMax(&skey[c0], ((unsigned long long)__float_as_uint(a) << 32) | lo);
+        if (c0 + 1 < C && b > eps) atomicMax(&skey[c0 + 1], ((unsigned long long)__float_as_uint(b) << 32) | lo);
+      }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(y + ((size_t)n * HW + p) * 32 + half_id * 16);
+    dst[0] = *reinterpret_cast<const uint4*>(&h[0]);
+    dst[1] = *reinterpret_cast<const uint4*>(&h[4]);
+  }
+  if (ARGMAX) {
+    __syncthreads();
+    if (threadIdx.x >= 1 && threadIdx.x < C && skey[threadIdx.x] != 0ull)
+      atomicMax(&keys[(size_t)n * (C - 1) + (threadIdx.x - 1)], skey[threadIdx.x]);
+  }
+}
+
+// packed arg-max keys -> (x, y) pixel of the maximum (or -1, -1) and visibility, like utils/label_conversions.py:142-153
+__global__ void argmax_decode_kernel(const unsigned long long* __restrict__ keys, int n, int W, float* __restrict__ j2d,
+                                     int* __restrict__ vis) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = keys[i];
+  const bool v = k != 0ull;
+  const unsigned idx = 0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull);
+  j2d[2 * i] = v ? (float)(idx % (unsigned)W) : -1.f;
+  j2d[2 * i + 1] = v ? floorf((float)idx / (float)W) : -1.f;
+  vis[i] = v ? 1 : 0;
 }
 
 __global__ void __launch_bounds__(256) maxpool3x3s2_f16_kernel(const __half* __restrict__ in, int H, int W, int C, int Ho,
@@ -956,11 +990,12 @@ void encoder_tc_destroy(void* p) {
 
 size_t encoder_tc_workspace_bytes(const void*, int B, int H, int W) {
   const int Bp = (B + 1) & ~1;   // layer4 tiles span two images
-  return act_bytes(Bp, H, W, 32) + act_bytes(Bp, H / 2, W / 2, 64) + 4 * act_bytes(Bp, H / 4, W / 4, 64);
+  return act_bytes(Bp, H, W, 32) + act_bytes(Bp, H / 2, W / 2, 64) + 4 * act_bytes(Bp, H / 4, W / 4, 64) +
+         align_up((size_t)B * 17 * 8, 1024);    // heat-map arg-max keys (encoder_tc_forward with an ArgmaxOut)
 }
 
 int encoder_tc_forward(const void* p, const float* x, int B, int H, int W, float* feats, void* workspace,
-                       size_t workspace_bytes, float* taps, cudaStream_t s, const ImageInput* image) {
+                       size_t workspace_bytes, float* taps, cudaStream_t s, const ImageInput* image, const ArgmaxOut* amax) {
   const EncoderTc* E = (const EncoderTc*)p;
   if (H != 256 || W != 256) { set_error("HP3D_ENC_FAST supports 256x256 proxy representations (DATA.PROXY_REP_SIZE)"); return -1; }
   const int Bp = (B + 1) & ~1;
@@ -973,8 +1008,16 @@ int encoder_tc_forward(const void* p, const float* x, int B, int H, int W, float
   if (image) {    // Canny edges + joint heat-maps written straight into the stem's fp16 NHWC(32) records (proxy.cu)
     rc = proxy_rep_nhwc32_f16(image->rgb, image->joints2d, image->visibility, B, H, image->gaussian_std, image->gaussian_size,
                               image->threshold, image->nms, image->heat_std, xin, s);
+  } else if (amax) {
+    unsigned long long* keys = (unsigned long long*)((char*)workspace + encoder_tc_workspace_bytes(p, B, H, W) - align_up((size_t)B * 17 * 8, 1024));
+    HP3D_CUDA(cudaMemsetAsync(keys, 0, (size_t)B * 17 * 8, s));
+    nchw_f32_to_nhwc32_f16_kernel<true><<<dim3(cdiv(H * W, 128), B), 256, 0, s>>>(x, 18, H * W, xin, amax->eps, keys);
+    rc = launch_status("nchw_f32_to_nhwc32_f16_kernel");
+    if (rc) return rc;
+    argmax_decode_kernel<<<cdiv(B * 17, 128), 128, 0, s>>>(keys, B * 17, W, amax->joints2d_px, amax->vis);
+    rc = launch_status("argmax_decode_kernel");
   } else {
-    nchw_f32_to_nhwc32_f16_kernel<<<dim3(cdiv(H * W, 128), B), 256, 0, s>>>(x, 18, H * W, xin);
+    nchw_f32_to_nhwc32_f16_kernel<false><<<dim3(cdiv(H * W, 128), B), 256, 0, s>>>(x, 18, H * W, xin, 0.f, nullptr);
     rc = launch_status("nchw_f32_to_nhwc32_f16_kernel");
   }
   if (rc) return rc;

@@ -294,6 +294,21 @@ extern "C" int hp3d_encoder_forward_image(const hp3d_encoder* h, const float* rg
   return encoder_tc_forward(h->tc, nullptr, B, img_wh, img_wh, feats, workspace, workspace_bytes, nullptr, (cudaStream_t)stream_, &im);
 }
 
+extern "C" int hp3d_encoder_forward_argmax(const hp3d_encoder* h, const float* x, int B, int H, int W, float* feats,
+                                           void* workspace, size_t workspace_bytes, float eps, float* joints2d_px,
+                                           int32_t* vis, void* stream_) {
+  HP3D_ARG(h && x && feats && workspace && joints2d_px && vis, "null argument");
+  if (h->mode == HP3D_ENC_FAST) {
+    HP3D_ARG(B > 0 && H >= 32 && W >= 32 && H % 32 == 0 && W % 32 == 0, "H and W must be multiples of 32");
+    HP3D_ARG(workspace_bytes >= hp3d_encoder_workspace_bytes(h, B, H, W), "workspace too small");
+    const ArgmaxOut am = {eps, joints2d_px, vis};
+    return encoder_tc_forward(h->tc, x, B, H, W, feats, workspace, workspace_bytes, nullptr, (cudaStream_t)stream_, nullptr, &am);
+  }
+  int rc = heatmap_argmax(x + (size_t)H * W, (long long)18 * H * W, B, H, W, eps, joints2d_px, vis, (cudaStream_t)stream_);
+  if (rc) return rc;
+  return hp3d_encoder_forward_taps(h, x, B, H, W, feats, workspace, workspace_bytes, nullptr, stream_);
+}
+
 extern "C" int hp3d_encoder_forward_taps(const hp3d_encoder* h, const float* x, int B, int H, int W, float* feats,
                                          void* workspace, size_t workspace_bytes, float* taps, void* stream_) {
   HP3D_ARG(h && x && feats && workspace, "null argument");

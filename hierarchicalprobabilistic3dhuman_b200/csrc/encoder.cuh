@@ -12,8 +12,14 @@ struct ImageInput {
   const float* rgb; const float* joints2d; const unsigned char* visibility;
   float gaussian_std; int gaussian_size; float threshold; int nms; float heat_std;
 };
+// optional by-product of the input cast: arg-max pixel / visibility of the 17 joint heat-maps (channels 1..17)
+struct ArgmaxOut { float eps; float* joints2d_px; int* vis; };
 int encoder_tc_forward(const void* p, const float* x_nchw, int B, int H, int W, float* feats, void* workspace,
-                       size_t workspace_bytes, float* taps, cudaStream_t stream, const ImageInput* image = nullptr);
+                       size_t workspace_bytes, float* taps, cudaStream_t stream, const ImageInput* image = nullptr,
+                       const ArgmaxOut* argmax = nullptr);
+// rank.cu: stand-alone heat-map arg-max (17 maps per image, images `image_stride` floats apart)
+int heatmap_argmax(const float* heatmaps, long long image_stride, int B, int H, int W, float eps, float* joints2d_px,
+                   int* vis, cudaStream_t stream);
 int proxy_rep_nhwc32_f16(const float* rgb, const float* joints2d, const unsigned char* visibility, int B, int img_wh,
                          float gaussian_std, int gaussian_size, float threshold, int nms, float heat_std, void* nhwc32,
                          cudaStream_t stream);

@@ -321,7 +321,10 @@ int blend_tc_forward(void* p, const float* betas, int Mb, const float* body_pose
   BlendArgs a;
   a.M = M; a.rep = M / Mb;
   a.m_tiles = cdiv(M, BM); a.n_tiles = NPAD / BN;
-  a.n_chunk = 18; a.n_chunks = cdiv(a.n_tiles, a.n_chunk);
+  // n-tiles per work unit (the A tile is re-fetched per unit): 18 amortises it for big M; small M (the mode meshes) gets
+  // short chunks so that every SM has a unit
+  a.n_chunk = std::max(1, std::min(18, cdiv(a.m_tiles * a.n_tiles, h->num_sms)));
+  a.n_chunks = cdiv(a.n_tiles, a.n_chunk);
   a.inv_scale = h->inv_scale; a.v_posed = v_posed;
   CUtensorMap tmOut;
   rc = make_tmap_f32_2d(&tmOut, v_posed, VPITCH, (uint64_t)M, (uint64_t)VPITCH * 4, 32, 32);

@@ -8,6 +8,7 @@
 //   3. ascending sort of the N errors per image (:228) -> sample order
 // The heat-maps are channels 1..17 of the proxy representation that is already on the device.
 #include "common.cuh"
+#include "encoder.cuh"
 #include <math_constants.h>
 
 using namespace hp3d;
@@ -89,6 +90,14 @@ __global__ void __launch_bounds__(256) rank_samples_kernel(const float* __restri
 }
 
 }  // namespace
+
+namespace hp3d {
+int heatmap_argmax(const float* heatmaps, long long image_stride, int B, int H, int W, float eps, float* joints2d_px,
+                   int* vis, cudaStream_t stream) {
+  heatmap_argmax_kernel<<<dim3(17, B), 256, 0, stream>>>(heatmaps, (size_t)image_stride, H * W, W, eps, joints2d_px, vis);
+  return launch_status("heatmap_argmax_kernel");
+}
+}  // namespace hp3d
 
 extern "C" int hp3d_rank_samples_by_joints2d(const float* joints, const float* heatmaps, long long heatmap_image_stride,
                                              const float* cam, int B, int N, int H, int W, float eps, int32_t* order,

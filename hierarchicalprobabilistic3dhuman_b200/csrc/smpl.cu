@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256) lbs_kernel(const float* __restrict__ v_po
 constexpr int TV = 64;                      // vertices per tile
 constexpr int NT = (NV + TV - 1) / TV;      // 108
 constexpr int NQCAP = 12;
-constexpr int LBS_G = 8;                    // meshes per CTA (== warps per CTA)
+constexpr int LBS_GMAX = 8;                 // meshes per CTA (<= warps per CTA); small batches use 2 so every SM gets a CTA
 constexpr int NU_MAX = NPICK + 255;         // unique vertices feeding the 66 extra joints (<= 276)
 constexpr int LBS_DEFAULT_MODE = 1;         // FFMA2 blending, 2 meshes ahead (see hp3d_smpl_lbs; profiles/r01i_lbs_sweep.jsonl)
 
@@ -291,8 +291,8 @@ struct LbsTileCtx {
   int tile, lane, m0, Gv, park0, park1;
   const float* v_posed; float* vertices;
   const int* tile_joff; const float* tile_w;
-  const float4* sA;     // [LBS_G][NJ*3]
-  float* sV;            // [LBS_G][NU_MAX][3]
+  const float4* sA;     // [G][NJ*3]
+  float* sV;            // [G][NU_MAX][3]
 };
 
 // Packed fp32 FMA (Blackwell FFMA2): acc.xy += s * v.xy in ONE issue slot; ptxas encodes the scalar as a
@@ -407,7 +407,7 @@ __device__ __forceinline__ void lbs_tile_body(const LbsTileCtx& c) {
   }
 }
 
-template <int NQMAX, bool F2, int PF>
+template <int NQMAX, bool F2, int PF, int LBS_G>
 __global__ void __launch_bounds__(256, 2) lbs_tile_kernel(const float* __restrict__ v_posed, const float* __restrict__ J,
                                                           int Mb, const float* __restrict__ global_orient, int Mg,
                                                           const float* __restrict__ body_pose, int M,
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(256, 2) lbs_tile_kernel(const float* __restric
   const int m0 = blockIdx.x * LBS_G;
   const int Gv = min(LBS_G, M - m0);
   // ---- phase 1: forward kinematics, warp g <-> mesh m0 + g
-  if (warp < Gv) {
+  if (warp < Gv) {   // LBS_G <= 8 warps
     const int m = m0 + warp, j = lane;
     float R[9], Jj[3] = {0.f, 0.f, 0.f}, rel[3] = {0.f, 0.f, 0.f};
     int par = -1, dep = 99;
@@ -886,12 +886,17 @@ extern "C" int hp3d_smpl_lbs(const hp3d_smpl* h, const float* v_posed, const flo
     // 3 = scalar FFMA, 4 ahead. Default: LBS_DEFAULT_MODE.
     static int mode = -1;
     if (mode < 0) { const char* e = getenv("HP3D_LBS_MODE"); mode = (e && *e >= '0' && *e <= '3') ? (*e - '0') : LBS_DEFAULT_MODE; }
-    const int grid = cdiv(M, LBS_G);
+    const int grid = cdiv(M, LBS_GMAX);
 #define HP3D_LBS_LAUNCH(NQM, F2, PF)                                                                                   \
-    lbs_tile_kernel<NQM, F2, PF><<<grid, 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M, \
+    lbs_tile_kernel<NQM, F2, PF, LBS_GMAX><<<grid, 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M, \
         h->tile_nq, h->tile_joff, h->tile_w, h->tile_ustart, h->tile_uent, h->reg_rowptr, h->reg_slot, h->reg_val,      \
         h->pick_slot, h->tree, vertices, joints)
-    if (h->tile_nq_max <= 8) {
+    if (h->tile_nq_max <= 8 && mode == 1 && grid < 148) {
+      // small batch (e.g. the B mode meshes): 2 meshes per CTA so the launch fills the GPU
+      lbs_tile_kernel<8, true, 2, 2><<<cdiv(M, 2), 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M,
+          h->tile_nq, h->tile_joff, h->tile_w, h->tile_ustart, h->tile_uent, h->reg_rowptr, h->reg_slot, h->reg_val,
+          h->pick_slot, h->tree, vertices, joints);
+    } else if (h->tile_nq_max <= 8) {
       switch (mode) {
         case 0: HP3D_LBS_LAUNCH(8, false, 2); break;
         case 1: HP3D_LBS_LAUNCH(8, true, 2); break;

@@ -47,11 +47,13 @@ class HotPathPipeline:
         self.chunks = chunks if B % chunks == 0 else 1
         self._stage = None
         self._slot = 0
-        # kernels launched by one pass (ResNet-18 fast mode 23, head 6, rot6d 1, SMPL 4+4, sampler 1, stats 1, betas copy 1)
-        self.launches_per_pass = 23 + 6 + 1 + 4 + 1 + (4 + 1) * len(self.vertex_chunks) + 1 + 2
+        # libhp3d kernels launched by one pass, counted on the ncu launch list (profiles/): encoder fast mode 24 (input cast,
+        # arg-max decode, stem, max-pool, 19 convolutions, avg-pool), head 6, rot6d 1, mode SMPL 4, sampler 1, per vertex chunk
+        # SMPL 4 + statistics 1, sample ranking 1
+        self.launches_per_pass = 24 + 6 + 1 + 4 + 1 + (4 + 1) * len(self.vertex_chunks) + 1
 
     # ------------------------------------------------------------------ device-resident pass
-    def _after_encoder(self, feats, proxy_rep=None, joints2d=None):
+    def _after_encoder(self, feats, proxy_rep=None, joints2d=None, joints2d_px=None):
         L, B, N = self.L, self.B, self.N
         F, U, S, V, mode, shape_params, glob, cam = self.net.head(feats)
         loc = shape_params[:, :10].contiguous()
@@ -72,17 +74,19 @@ class HotPathPipeline:
                 self.on_vertices_chunk(c)
         res = dict(mode_vertices=out_mode.vertices, mode_joints=out_mode.joints, joints=self.joints, rotmats=R,
                    uncertainty=self.uncertainty, vertices=self.vertices, betas=self.betas, pose_S=S, cam=cam)
-        if proxy_rep is not None or joints2d is not None:
+        if proxy_rep is not None or joints2d is not None or joints2d_px is not None:
             # rank the N samples of every image by 2D-joint consistency (sampling_utils.py:195-233)
             from .sampling import rank_samples_by_joints2d
-            rk = rank_samples_by_joints2d(self.joints.view(B, N, 90, 3), proxy_rep, cam, joints2d=joints2d)
+            rk = rank_samples_by_joints2d(self.joints.view(B, N, 90, 3), proxy_rep, cam, joints2d=joints2d, joints2d_px=joints2d_px,
+                                          img_wh=proxy_rep.shape[-1] if proxy_rep is not None else 256)
             res["sample_order"], res["sample_error"] = rk["order"], rk["error"]
         return res
 
     def run_device(self, x_dev):
         """x_dev (B,18,256,256) fp32 on the GPU -> dict of device tensors (sample vertices live in `vertices`)."""
         with torch.cuda.device(self.dev):
-            return self._after_encoder(self.net.encode(x_dev), x_dev)
+            feats, j2d, vis = self.net.encode(x_dev, return_joints2d=True)     # heat-map arg-max rides on the input pass
+            return self._after_encoder(feats, joints2d_px=(j2d, vis))
 
     def run_device_images(self, rgb, joints2D, visibility=None):
         """Image-space input: (B,3,256,256) RGB crops in [0,1], (B,17,2) joints, (B,17)
@@ -129,16 +133,18 @@ class HotPathPipeline:
                     e = torch.cuda.Event()
                     e.record(st["h2d"])
                     evs.append(e)
-            feats = []
+            feats, j2d, vis = [], [], []
             for c in range(C):
                 main.wait_event(evs[c])
-                feats.append(self.net.encode(xbuf[c * cb:(c + 1) * cb]))
+                f_, j_, v_ = self.net.encode(xbuf[c * cb:(c + 1) * cb], return_joints2d=True)
+                feats.append(f_); j2d.append(j_); vis.append(v_)
             free = torch.cuda.Event()
             free.record(main)
             st["x_free"][slot] = free
             if st["out_done"][slot ^ 1] is not None:
                 main.wait_event(st["out_done"][slot ^ 1])               # previous call's results have left the device buffers
-            res = self._after_encoder(torch.cat(feats) if C > 1 else feats[0], xbuf)
+            cat = lambda ts: torch.cat(ts) if C > 1 else ts[0]
+            res = self._after_encoder(cat(feats), joints2d_px=(cat(j2d), cat(vis)))
             done = torch.cuda.Event()
             done.record(main)
             out = st["out"][slot]

@@ -151,8 +151,10 @@ class PoseMFShapeGaussianNet(nn.Module):
         return enc, head
 
     # ------------------------------------------------------------------ stages
-    def encode(self, input):
-        """(B,18,H,W) fp32 NCHW on CUDA -> (B,512) features (reference models/resnet.py:202-217)."""
+    def encode(self, input, return_joints2d=False, eps=1e-6):
+        """(B,18,H,W) fp32 NCHW on CUDA -> (B,512) features (reference models/resnet.py:202-217).
+        return_joints2d=True additionally returns the arg-max pixel (B,17,2) and visibility (B,17) int32 of the joint
+        heat-maps in channels 1..17 (utils/label_conversions.py:127-155), a by-product of the input pass."""
         _lib.require_cuda(input, "input")
         dev = input.device
         key = dev.index if dev.index is not None else torch.cuda.current_device()
@@ -165,6 +167,13 @@ class PoseMFShapeGaussianNet(nn.Module):
         with torch.cuda.device(dev):
             nbytes = L.hp3d_encoder_workspace_bytes(enc, B, H, W)
             ws = self._ws.get(nbytes, dev)
+            if return_joints2d:
+                j2d = torch.empty(B, 17, 2, device=dev, dtype=torch.float32)
+                vis = torch.empty(B, 17, device=dev, dtype=torch.int32)
+                _lib.check(L.hp3d_encoder_forward_argmax(enc, x.data_ptr(), B, H, W, feats.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                         float(eps), j2d.data_ptr(), vis.data_ptr(), _lib.stream_ptr()),
+                           "hp3d_encoder_forward_argmax")
+                return feats, j2d, vis
             _lib.check(L.hp3d_encoder_forward(enc, x.data_ptr(), B, H, W, feats.data_ptr(), ws.data_ptr(), ws.numel(),
                                               _lib.stream_ptr()), "hp3d_encoder_forward")
         return feats

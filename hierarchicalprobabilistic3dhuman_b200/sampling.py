@@ -85,12 +85,14 @@ def compute_vertex_uncertainties_by_poseMF_shapeGaussian_sampling(pose_U, pose_S
     return dist[0], out.vertices, out.joints
 
 
-def rank_samples_by_joints2d(joints_samples, proxy_rep_or_heatmaps, cam_wp, eps=1e-6, joints2d=None, img_wh=256, std=4.0):
+def rank_samples_by_joints2d(joints_samples, proxy_rep_or_heatmaps, cam_wp, eps=1e-6, joints2d=None, img_wh=256, std=4.0,
+                             joints2d_px=None):
     """Batched core of the reference's `joints2D_error_sorted_verts_sampling` (utils/sampling_utils.py:195-233):
     joints_samples (B,N,90,3), proxy representation (B,18,H,W) or heat-maps (B,17,H,W), cam_wp (B,3) ->
     dict(order (B,N) int64 sample indices by ascending 2D-joint error, error (B,N), joints2d (B,17,2), vis (B,17)).
     Image-space path: pass `joints2d=(joints2D (B,17,2), visibility (B,17) or None)` and None for the heat-maps; their
-    arg-max is then computed without materialising them (hp3d_joints2d_heatmap_argmax)."""
+    arg-max is then computed without materialising them (hp3d_joints2d_heatmap_argmax). `joints2d_px=(px (B,17,2),
+    vis (B,17) int32)` passes an arg-max that is already known (`PoseMFShapeGaussianNet.encode(..., return_joints2d=True)`)."""
     _lib.require_cuda(joints_samples, "joints_samples")
     dev = joints_samples.device
     J = joints_samples.detach().to(torch.float32).contiguous()
@@ -98,7 +100,11 @@ def rank_samples_by_joints2d(joints_samples, proxy_rep_or_heatmaps, cam_wp, eps=
     cam = cam_wp.detach().to(device=dev, dtype=torch.float32).contiguous()
     order = torch.empty(B, N, device=dev, dtype=torch.int32)
     err = torch.empty(B, N, device=dev, dtype=torch.float32)
-    if joints2d is not None:
+    if joints2d_px is not None:
+        j2d, vis = joints2d_px[0].contiguous(), joints2d_px[1].to(torch.int32).contiguous()
+        assert j2d.shape == (B, 17, 2) and j2d.dtype == torch.float32
+        hm_ptr, stride, H, W = None, 0, img_wh, img_wh
+    elif joints2d is not None:
         from .proxy import joints2d_heatmap_argmax
         j2d, vis = joints2d_heatmap_argmax(joints2d[0], joints2d[1], img_wh, std, eps)
         assert j2d.shape == (B, 17, 2)

@@ -169,6 +169,12 @@ size_t hp3d_encoder_workspace_bytes(const hp3d_encoder* h, int B, int H, int W);
 /* x [B*18*H*W] fp32 NCHW (the reference's input layout, predict/...:100) -> feats [B*512] */
 int hp3d_encoder_forward(const hp3d_encoder* h, const float* x_nchw, int B, int H, int W, float* feats,
                          void* workspace, size_t workspace_bytes, void* stream);
+/* hp3d_encoder_forward that also returns the arg-max pixel (x, y; -1 if max <= eps) and visibility of the 17 joint
+ * heat-maps in channels 1..17 (utils/label_conversions.py:127-155), a by-product of the input pass in fast mode:
+ * joints2d_px [B*17*2], vis [B*17] -- the inputs hp3d_rank_samples_by_joints2d accepts with heatmaps == NULL. */
+int hp3d_encoder_forward_argmax(const hp3d_encoder* h, const float* x_nchw, int B, int H, int W, float* feats,
+                                void* workspace, size_t workspace_bytes, float eps, float* joints2d_px, int32_t* vis,
+                                void* stream);
 /* image-space entry (HP3D_ENC_FAST handles only): rgb [B*3*256*256] in [0,1], joints2d [B*17*2], visibility [B*17]
  * bytes or NULL -> feats. The Canny + heat-map kernel writes the stem's fp16 NHWC input records directly: the fp32
  * proxy representation of predict/...:100 never exists in memory. Same workspace as hp3d_encoder_forward. */

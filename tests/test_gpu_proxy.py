@@ -135,3 +135,24 @@ def test_pipeline_from_images_matches_proxy_path(built_lib):
     out, ev = pipe.run_host_images(rgb.pin_memory(), j2d.pin_memory(), vis.to(torch.uint8).pin_memory())
     ev.synchronize()
     assert rel_err(out["mode_vertices"], b["mode_vertices"]) < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["fast", "parity"])
+def test_encoder_argmax_byproduct(built_lib, mode):
+    """encode(..., return_joints2d=True): heat-map arg-max fused into the input pass == the reference's
+    convert_heatmaps_to_2Djoints_coordinates_torch (pinned oracle), features unchanged."""
+    import hierarchicalprobabilistic3dhuman_b200 as hp
+    from hierarchicalprobabilistic3dhuman_b200 import synthetic as syn
+    from oracle import sampler_oracle
+    x = torch.from_numpy(syn.synthetic_proxy_rep(5, seed=5))
+    x[1, 3] = 0.0                                   # an all-zero heat-map: invisible joint
+    x[2, 4] = 1e-7                                  # below eps everywhere: invisible too
+    x[3, 5, 10:12, 20:22] = 0.75                    # a 4-way tie: first index wins
+    net = hp.PoseMFShapeGaussianNet(syn.SMPL_PARENTS.tolist(), reference_config(), encoder_mode=mode)
+    net.load_state_dict(syn.synthetic_state_dict(0))
+    net = net.cuda().eval()
+    feats, j2d, vis = net.encode(x.cuda(), return_joints2d=True)
+    ref_j2d, ref_vis = sampler_oracle.heatmaps_to_joints2d(x[:, 1:])
+    assert torch.equal(j2d.cpu(), ref_j2d) and torch.equal(vis.cpu() != 0, ref_vis)
+    assert not ref_vis[1, 2] and not ref_vis[2, 3] and ref_j2d[3, 4].tolist() == [20.0, 10.0]
+    assert torch.equal(feats, net.encode(x.cuda()))
