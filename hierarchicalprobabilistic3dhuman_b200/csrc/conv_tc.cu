@@ -580,37 +580,47 @@ __global__ void __launch_bounds__(256) nchw_f32_to_nhwc32_f16_kernel(const float
                                                                      unsigned long long* __restrict__ keys) {
   // thread = (pixel, 16-channel half): 16 (or C-16) coalesced plane reads -> one full 32-byte sector of the
   // NHWC record (two 16-byte stores); channels >= C are written as zero padding.
-  __shared__ unsigned long long skey[32];
   const int n = blockIdx.y;
   const int p = blockIdx.x * 128 + (threadIdx.x & 127);
-  const int half_id = threadIdx.x >> 7;               // 0: channels 0..15, 1: channels 16..31
-  if (ARGMAX) {
-    if (threadIdx.x < 32) skey[threadIdx.x] = 0ull;
-    __syncthreads();
-  }
-  if (p < HW) {
-    const float* src = x + (size_t)n * C * HW + p;
-    __half2 h[8];
+  const int half_id = threadIdx.x >> 7;               // 0: channels 0..15, 1: channels 16..31 (warp-uniform)
+  const bool valid = p < HW;
+  const float* src = x + (size_t)n * C * HW + (valid ? p : 0);
+  __half2 h[8];
+  float v[16];
+  unsigned candmask = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c0 = half_id * 16 + 2 * k;
-      const float a = (c0 < C) ? src[(size_t)c0 * HW] : 0.f;
-      const float b = (c0 + 1 < C) ? src[(size_t)(c0 + 1) * HW] : 0.f;
-      h[k] = __floats2half2_rn(a, b);
-      if (ARGMAX) {
-        const unsigned long long lo = (unsigned long long)(0xFFFFFFFFu - (unsigned)p);
-        if (c0 >= 1 && c0 < C && a > eps) atomicMax(&skey[c0], ((unsigned long long)__float_as_uint(a) << 32) | lo);
-        if (c0 + 1 < C && b > eps) atomicMax(&skey[c0 + 1], ((unsigned long long)__float_as_uint(b) << 32) | lo);
-      }
+  for (int k = 0; k < 8; ++k) {
+    const int c0 = half_id * 16 + 2 * k;
+    v[2 * k] = (valid && c0 < C) ? src[(size_t)c0 * HW] : 0.f;
+    v[2 * k + 1] = (valid && c0 + 1 < C) ? src[(size_t)(c0 + 1) * HW] : 0.f;
+    h[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+    if (ARGMAX) {
+      candmask |= (c0 >= 1 && v[2 * k] > eps) ? (1u << (2 * k)) : 0u;       // channels >= C were loaded as 0
+      candmask |= (v[2 * k + 1] > eps) ? (2u << (2 * k)) : 0u;
     }
+  }
+  if (valid) {
     uint4* dst = reinterpret_cast<uint4*>(y + ((size_t)n * HW + p) * 32 + half_id * 16);
     dst[0] = *reinterpret_cast<const uint4*>(&h[0]);
     dst[1] = *reinterpret_cast<const uint4*>(&h[4]);
   }
   if (ARGMAX) {
-    __syncthreads();
-    if (threadIdx.x >= 1 && threadIdx.x < C && skey[threadIdx.x] != 0ull)
-      atomicMax(&keys[(size_t)n * (C - 1) + (threadIdx.x - 1)], skey[threadIdx.x]);
+    // heat-map values above eps are rare (one Gaussian blob per map): most warps leave after a single vote; the others
+    // reduce (value, lowest pixel) over their lanes per candidate channel and post ONE global atomicMax each
+    unsigned any = __reduce_or_sync(0xffffffffu, candmask);
+    while (any) {
+      const int e = __ffs(any) - 1;
+      any &= any - 1;
+      const bool cand = (candmask >> e) & 1u;
+      unsigned hi = cand ? __float_as_uint(v[e]) : 0u, lo = cand ? (0xFFFFFFFFu - (unsigned)p) : 0u;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned ohi = __shfl_xor_sync(0xffffffffu, hi, o), olo = __shfl_xor_sync(0xffffffffu, lo, o);
+        if (ohi > hi || (ohi == hi && olo > lo)) { hi = ohi; lo = olo; }
+      }
+      const int c = half_id * 16 + e;
+      if ((threadIdx.x & 31) == 0) atomicMax(&keys[(size_t)n * (C - 1) + (c - 1)], ((unsigned long long)hi << 32) | lo);
+    }
   }
 }
 

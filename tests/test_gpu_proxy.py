@@ -147,6 +147,7 @@ def test_encoder_argmax_byproduct(built_lib, mode):
     x = torch.from_numpy(syn.synthetic_proxy_rep(5, seed=5))
     x[1, 3] = 0.0                                   # an all-zero heat-map: invisible joint
     x[2, 4] = 1e-7                                  # below eps everywhere: invisible too
+    x[3, 5] = 0.0
     x[3, 5, 10:12, 20:22] = 0.75                    # a 4-way tie: first index wins
     net = hp.PoseMFShapeGaussianNet(syn.SMPL_PARENTS.tolist(), reference_config(), encoder_mode=mode)
     net.load_state_dict(syn.synthetic_state_dict(0))
