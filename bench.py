@@ -44,8 +44,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="one warm-up + the timed steps only (for ncu): no e2e / LBS-alone / CPU legs")
     ap.add_argument("--ref-threads", type=int, default=0, help="torch CPU threads for the reference arm (0 = pick the best of a sweep)")
-    ap.add_argument("--transport", default="nccl", choices=["p2p", "nccl"],
-                    help="N>1 vertices gather: NCCL (default) or EXPERIMENTAL copy-engine peer pushes over CUDA IPC")
+    ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"],
+                    help="N>1 vertices gather: copy-engine peer pushes over symmetric memory (p2p), NCCL all-gather, or "
+                         "auto = p2p when the symmetric-memory rendezvous works, else NCCL")
     ap.add_argument("--gather", default="full", choices=["full", "stats"],
                     help="N>1: all-gather (rotmats, betas, vertices) [configs[3]] or per-image statistics only")
     return ap.parse_args()
@@ -198,7 +199,15 @@ def main_hp3d(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # the gather's NCCL kernels must squeeze in next to kernels that fill every SM: run them on a high-priority
+        # stream (their CTAs are placed first whenever an SM frees up) and cap their CTA count (HP3D_NCCL_CTAS, 0 = NCCL default)
+        ctas = os.environ.get("HP3D_NCCL_CTAS", "16")
+        if ctas != "0":
+            os.environ.setdefault("NCCL_MAX_CTAS", ctas)
+        opts = None
+        if os.environ.get("HP3D_NCCL_PRIO", "1") == "1":
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     B, N = args.batch, args.samples
     import __graft_entry__
     if rank == 0:
@@ -226,19 +235,22 @@ def main_hp3d(args):
     cbv = B // VC
     # two buffer sets: the NVLink gather of step i also overlaps the encoder of step i+1
     NBUF = 2 if (full and world > 1) else 1
-    g_verts = [torch.empty(VC, world if full else 1, cbv, N, 6890, 3, device=dev) for _ in range(NBUF)]
+    from hierarchicalprobabilistic3dhuman_b200.distributed import SymmPush
+    pushers = None
+    if world > 1 and full and args.transport in ("auto", "p2p"):
+        pushers = [SymmPush((VC, world, cbv, N, 6890, 3), dev, rank, world) for _ in range(NBUF)]
+        g_verts = [p_.full for p_ in pushers]
+        if not all(p_.ok for p_ in pushers):
+            if rank == 0:
+                print("symmetric-memory transport unavailable, using NCCL:", pushers[0].error, file=sys.stderr)
+            pushers = None
+    else:
+        g_verts = [torch.empty(VC, world if full else 1, cbv, N, 6890, 3, device=dev) for _ in range(NBUF)]
     my = rank if full else 0
     comm_stream = torch.cuda.Stream(device=dev)
     state = {"k": 0, "pending": [None] * NBUF, "count": 0}
 
-    # transport of the big vertices gather: peer-to-peer pushes on the copy engines (no SMs) if CUDA IPC works
-    from hierarchicalprobabilistic3dhuman_b200.distributed import PeerPush
-    pushers = None
-    if world > 1 and full and args.transport == "p2p":
-        pushers = [PeerPush(g, rank, world) for g in g_verts]
-        if not all(p_.ok for p_ in pushers):
-            pushers = None
-    transport = "p2p-copy-engine" if pushers else ("nccl" if (world > 1 and full) else "none")
+    transport = "p2p-copy-engine (symmetric memory)" if pushers else ("nccl" if (world > 1 and full) else "none")
 
     def on_chunk(c):
         if world > 1 and full:
@@ -310,10 +322,23 @@ def main_hp3d(args):
     sync_all()
     clk.on.clear()
     ms = e0.elapsed_time(e1) / args.steps
+    # ---- one-off check of the vertices gather (outside the timed regions): the slices received from the peers must carry
+    #      the peers' data -- compare per-slice checksums with the ones each producer computes locally
+    gather_ok = None
+    if world > 1 and full:
+        kbuf = state["k"]
+        mine = g_verts[kbuf][:, my].double().sum().reshape(1)
+        sums = torch.empty(world, device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(sums, mine)
+        got = torch.stack([g_verts[kbuf][:, r].double().sum() for r in range(world)])
+        gather_ok = bool(((got - sums).abs() <= 1e-9 * sums.abs().clamp_min(1.0)).all().item())
+        assert gather_ok, f"rank {rank}: gathered vertex slices do not match their producers ({got.tolist()} vs {sums.tolist()})"
     if args.profile:
         clk.__exit__()
         if rank == 0:
-            print(json.dumps({"profile_ms_per_step": ms}))
+            print(json.dumps({"profile_ms_per_step": ms, "transport": transport, "gather_verified": gather_ok}))
+        if world > 1:
+            dist.destroy_process_group()
         return
 
     # ---- end to end through the public API: pinned host input -> chunked H2D overlapped with the encoder ->
@@ -404,7 +429,7 @@ def main_hp3d(args):
                 "data": "synthetic",
                 "config": {"workload": f"BASELINE configs[1]/[3] at the metric's batch: {B} images/GPU x N={N} samples, 18x256x256 proxy rep, "
                                        f"full hot path (encoder+head+sampler+SMPL on {B * N} meshes/GPU)",
-                           "encoder_mode": args.encoder_mode, "gather": args.gather if world > 1 else "none", "gather_transport": transport,
+                           "encoder_mode": args.encoder_mode, "gather": args.gather if world > 1 else "none", "gather_transport": transport, "gather_verified": gather_ok,
                            "l2": "inputs (1.2 GB/step) and outputs (2.1 GB/step) exceed the 126 MB L2; no explicit flush",
                            "smpl": "synthetic SMPL-shaped model (licence-gated file absent)", "rng": "in-kernel Philox"},
                 "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s",
