@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"],
                     help="N>1 vertices gather: copy-engine peer pushes over symmetric memory (p2p), NCCL all-gather, or "
                          "auto = p2p when the symmetric-memory rendezvous works, else NCCL")
+    ap.add_argument("--sm-limit", type=int, default=-1,
+                    help="CTAs of the persistent tensor-core kernels (experiment: leave SMs to a co-running NCCL gather; "
+                         "-1 / 0 = all SMs, the default -- 116 of 148 brought nothing at 4 GPUs)")
     ap.add_argument("--gather", default="full", choices=["full", "stats"],
                     help="N>1: all-gather (rotmats, betas, vertices) [configs[3]] or per-image statistics only")
     return ap.parse_args()
@@ -201,7 +204,7 @@ def main_hp3d(args):
     if world > 1:
         # the gather's NCCL kernels must squeeze in next to kernels that fill every SM: run them on a high-priority
         # stream (their CTAs are placed first whenever an SM frees up) and cap their CTA count (HP3D_NCCL_CTAS, 0 = NCCL default)
-        ctas = os.environ.get("HP3D_NCCL_CTAS", "16")
+        ctas = os.environ.get("HP3D_NCCL_CTAS", "0")      # capping NCCL's CTAs only slowed the gather (2 GPUs: 8.9 / 11.2 / 16.8 ms at default / 16 / 8)
         if ctas != "0":
             os.environ.setdefault("NCCL_MAX_CTAS", ctas)
         opts = None
@@ -237,7 +240,14 @@ def main_hp3d(args):
     NBUF = 2 if (full and world > 1) else 1
     from hierarchicalprobabilistic3dhuman_b200.distributed import SymmPush
     pushers = None
-    if world > 1 and full and args.transport in ("auto", "p2p"):
+    # transport policy (measured, profiles/README.md): 2 GPUs -> copy-engine pushes (6.5 vs 8.8 ms/step); >= 4 GPUs -> NCCL
+    # (14.7 vs 16.0 ms/step at 4 GPUs: the step is bound by the 6.4 GB each rank receives, NCCL moves it faster)
+    want_p2p = args.transport == "p2p" or (args.transport == "auto" and world == 2)
+    if world > 1 and full and not want_p2p:
+        lim = args.sm_limit
+        if lim > 0:
+            os.environ["HP3D_SM_LIMIT"] = str(lim)
+    if world > 1 and full and want_p2p:
         pushers = [SymmPush((VC, world, cbv, N, 6890, 3), dev, rank, world) for _ in range(NBUF)]
         g_verts = [p_.full for p_ in pushers]
         if not all(p_.ok for p_ in pushers):
@@ -430,6 +440,7 @@ def main_hp3d(args):
                 "config": {"workload": f"BASELINE configs[1]/[3] at the metric's batch: {B} images/GPU x N={N} samples, 18x256x256 proxy rep, "
                                        f"full hot path (encoder+head+sampler+SMPL on {B * N} meshes/GPU)",
                            "encoder_mode": args.encoder_mode, "gather": args.gather if world > 1 else "none", "gather_transport": transport, "gather_verified": gather_ok,
+                           "persistent_kernel_ctas": int(os.environ.get("HP3D_SM_LIMIT", "0")) or "all SMs",
                            "l2": "inputs (1.2 GB/step) and outputs (2.1 GB/step) exceed the 126 MB L2; no explicit flush",
                            "smpl": "synthetic SMPL-shaped model (licence-gated file absent)", "rng": "in-kernel Philox"},
                 "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s",

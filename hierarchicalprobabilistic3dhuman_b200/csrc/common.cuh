@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include "../../include/hp3d.h"
 
 namespace hp3d {
@@ -49,6 +50,14 @@ int upload(T** dptr, const T* host, size_t n) {
 }
 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+// CTAs a persistent one-CTA-per-SM kernel may launch: the SM count, or HP3D_SM_LIMIT if set lower (multi-GPU runs leave a
+// few SMs to the NCCL all-gather kernels, which otherwise cannot start until a whole persistent kernel has drained and
+// then stall a statically partitioned successor)
+inline int persistent_ctas(int num_sms) {
+  const char* e = getenv("HP3D_SM_LIMIT");
+  const int lim = e ? atoi(e) : 0;
+  return (lim > 0 && lim < num_sms) ? lim : num_sms;
+}
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace hp3d

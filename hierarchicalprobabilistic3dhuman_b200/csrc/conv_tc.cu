@@ -960,6 +960,7 @@ int encoder_tc_create(const hp3d_encoder_weights* w, void** out) {
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&E->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  E->num_sms = persistent_ctas(E->num_sms);
   int rc = make_tc_conv(w->stem, w->bn_eps, true, E->stem);
   const int planes[4] = {64, 128, 256, 512};
   int inpl = 64;

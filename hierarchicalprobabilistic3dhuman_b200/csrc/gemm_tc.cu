@@ -258,6 +258,7 @@ int blend_tc_create(const double* posedirs, const double* shapedirs, const doubl
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  h->num_sms = persistent_ctas(h->num_sms);
   const char* e = getenv("HP3D_BLEND_PASSES");
   h->passes = (e && atoi(e) == 1) ? 1 : 3;
   double mx = 0.0;
