@@ -455,9 +455,9 @@ def main_hp3d(args):
                                             "NOT the metric's input contract -- reported beside `e2e`, which is"},
                 "gpu_launches": launches,
                 "clocks": clocks,
-                "roofline": {"kernel": "lbs_kernel (SMPL FK + skinning + 90 joints)", "bound": "hbm", "achieved": achieved,
+                "roofline": {"kernel": "lbs_tile_kernel (SMPL FK + skinning + 90 joints)", "bound": "hbm", "achieved": achieved,
                              "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                             "traffic": 4.2932e9 if M == 25600 else None, "traffic_source": "profiles/r01d_ncu_full_summary.csv (dram read 2.1476 GB + write 2.1456 GB per launch at 25,600 meshes)",
+                             "traffic": 4.2867e9 if M == 25600 else None, "traffic_source": "profiles/r01p_ncu_full_summary.csv (ncu --set full: dram read 2.1436 GB + write 2.1431 GB per launch at 25,600 meshes)",
                              "ms": lbs_ms, "meshes": M, "bytes_per_mesh": LBS_BYTES_PER_MESH}}
         if not args.no_cpu_baseline and world == 1:
             cb, _ = time_cpu_reference(2, 1, args.ref_batch, N)
