@@ -610,6 +610,7 @@ __global__ void __launch_bounds__(256) vertex_uncertainty_kernel(const float* __
 // Single-read variant: a CTA stages ALL N samples of 64 consecutive vertices (N x 768 B, contiguous per sample)
 // in shared memory with one coalesced pass over HBM, then computes the mean and the mean distance from it out of
 // shared memory. Halves the HBM traffic of the two-pass kernel above (which remains the fallback for N > 280).
+constexpr int UNC_DEFAULT_VARIANT = 3;     // 64-vertex tiles staged by cp.async: 0.50 ms vs 0.52 (variant 1) / 0.63 (variant 2)
 constexpr int UNC_TV = 32;                 // vertices per CTA: 96 floats (384 B) per sample, N x 384 B of shared memory
 constexpr int UNC_F = UNC_TV * 3;
 __global__ void __launch_bounds__(256) vertex_uncertainty_smem_kernel(const float* __restrict__ verts, int B, int N,
@@ -668,6 +669,91 @@ __global__ void __launch_bounds__(256) vertex_uncertainty_smem_kernel(const floa
     float a = 0.f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) a += part[q * 32 + t];
+    dist_out[(size_t)b * NV + v0 + t] = a / (float)N;
+    if (mean_out) {
+      float* mo = mean_out + ((size_t)b * NV + v0 + t) * 3;
+      mo[0] = mean[3 * t]; mo[1] = mean[3 * t + 1]; mo[2] = mean[3 * t + 2];
+    }
+  }
+}
+
+// 64-vertex variant with 8-byte loads: a sample row of the tile is 192 floats = 96 float2 (rows start 8-byte aligned:
+// 82,680 = 8 * 10,335 and 64 vertices = 768 B), three coalesced 256-byte loads per warp instead of six 128-byte ones,
+// half the load / shared-store instructions per byte. N x 768 B of shared memory (2 CTAs/SM at N = 100).
+constexpr int UNC2_TV = 64;
+constexpr int UNC2_F = UNC2_TV * 3;        // 192
+// ASYNC: stage with 8-byte cp.async (LDGSTS) instead of register round trips: no registers or STS per byte and every row
+// of the tile is in flight at once (ptxas interleaves the register variant's loads and stores in groups of ~8).
+template <bool ASYNC>
+__global__ void __launch_bounds__(256) vertex_uncertainty_smem2_kernel(const float* __restrict__ verts, int B, int N,
+                                                                       float* __restrict__ mean_out,
+                                                                       float* __restrict__ dist_out) {
+  extern __shared__ __align__(8) float us2[];          // [N][192] samples | [192] mean | [4][64] partial distances
+  const int b = blockIdx.y, v0 = blockIdx.x * UNC2_TV;
+  const int nv = min(UNC2_TV, NV - v0);                // 64, last tile 42 (even: whole float2s)
+  const int nf2 = nv * 3 / 2;                          // float2s per sample row in this tile
+  const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+  float* mean = us2 + (size_t)N * UNC2_F;
+  float* part = mean + UNC2_F;
+  const float* base = verts + (size_t)b * N * NV3 + (size_t)v0 * 3;
+  if (ASYNC) {
+    for (int n = w; n < N; n += 8) {
+      const float* row = base + (size_t)n * NV3;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int f = lane + 32 * i;
+        if (f < nf2) {
+          const unsigned dst = (unsigned)__cvta_generic_to_shared(us2 + (size_t)n * UNC2_F + 2 * f);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(row + 2 * f) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else
+  for (int n0 = w; n0 < N; n0 += 64) {                 // warp w stages samples w, w+8, ...; eight rows in flight
+    float2 r[8][3];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int n = n0 + 8 * u;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const int f = lane + 32 * i;
+        r[u][i] = (n < N && f < nf2) ? reinterpret_cast<const float2*>(base + (size_t)n * NV3)[f] : make_float2(0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int n = n0 + 8 * u;
+      if (n < N) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) reinterpret_cast<float2*>(us2 + (size_t)n * UNC2_F)[lane + 32 * i] = r[u][i];
+      }
+    }
+  }
+  __syncthreads();
+  if (t < UNC2_F) {
+    float s0 = 0.f, s1 = 0.f;
+    int n = 0;
+    for (; n + 1 < N; n += 2) { s0 += us2[n * UNC2_F + t]; s1 += us2[(n + 1) * UNC2_F + t]; }
+    if (n < N) s0 += us2[n * UNC2_F + t];
+    mean[t] = (s0 + s1) / (float)N;
+  }
+  __syncthreads();
+  {
+    const int v = t & 63, q = t >> 6;                  // 4 sample groups x 64 vertices
+    const float mx = mean[3 * v], my = mean[3 * v + 1], mz = mean[3 * v + 2];
+    float acc = 0.f;
+    for (int n = q; n < N; n += 4) {
+      const float* p = us2 + n * UNC2_F + 3 * v;
+      const float dx = p[0] - mx, dy = p[1] - my, dz = p[2] - mz;
+      acc += sqrtf(dx * dx + dy * dy + dz * dz);
+    }
+    part[q * 64 + v] = acc;
+  }
+  __syncthreads();
+  if (t < nv) {
+    const float a = (part[t] + part[64 + t]) + (part[128 + t] + part[192 + t]);
     dist_out[(size_t)b * NV + v0 + t] = a / (float)N;
     if (mean_out) {
       float* mo = mean_out + ((size_t)b * NV + v0 + t) * 3;
@@ -948,6 +1034,21 @@ extern "C" int hp3d_rot6d_to_rotmat(const float* x, int n, float* R, void* strea
 extern "C" int hp3d_vertex_uncertainty(const float* vertices, int B, int N, float* mean_vertices, float* avg_dist,
                                        void* stream) {
   HP3D_ARG(vertices && avg_dist && B > 0 && N > 0, "bad argument");
+  static int variant = -1;       // HP3D_UNC: 1 = 32-vertex tiles, 4-byte loads; 2 = 64-vertex tiles, 8-byte loads; 3 = 64-vertex tiles, cp.async
+  if (variant < 0) { const char* e = getenv("HP3D_UNC"); variant = (e && *e >= '1' && *e <= '3') ? (*e - '0') : UNC_DEFAULT_VARIANT; }
+  const size_t smem2 = ((size_t)N * UNC2_F + UNC2_F + 256) * sizeof(float);
+  if (variant >= 2 && smem2 <= 110 * 1024) {
+    static size_t attr2[2] = {0, 0};
+    dim3 grid(cdiv(NV, UNC2_TV), B);
+    if (variant == 2) {
+      if (smem2 > attr2[0]) { HP3D_CUDA(cudaFuncSetAttribute(vertex_uncertainty_smem2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); attr2[0] = smem2; }
+      vertex_uncertainty_smem2_kernel<false><<<grid, 256, smem2, (cudaStream_t)stream>>>(vertices, B, N, mean_vertices, avg_dist);
+    } else {
+      if (smem2 > attr2[1]) { HP3D_CUDA(cudaFuncSetAttribute(vertex_uncertainty_smem2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); attr2[1] = smem2; }
+      vertex_uncertainty_smem2_kernel<true><<<grid, 256, smem2, (cudaStream_t)stream>>>(vertices, B, N, mean_vertices, avg_dist);
+    }
+    return launch_status("vertex_uncertainty_smem2_kernel");
+  }
   const size_t smem = ((size_t)N * UNC_F + UNC_F + 256) * sizeof(float);
   if (smem <= 220 * 1024) {
     static size_t attr = 0;

@@ -74,6 +74,8 @@ class SymmPush:
         """Copies ordered after the work already enqueued on `stream`; `stream` then waits for them. One device-to-device
         copy runs on one copy engine (~320 GB/s measured), so the (peer, sub-slice) copies are spread over
         `num_streams` streams to keep several engines -- and all NVLink lanes -- busy."""
+        if not self.ok:
+            return                                  # fallback mode: the caller gathers with NCCL / gloo
         src = view_fn(self.full)
         if self._streams is None:
             self._streams = [torch.cuda.Stream(device=self.full.device) for _ in range(self.num_streams)]

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from hierarchicalprobabilistic3dhuman_b200.distributed import shard_range, GatherBuffers
+from hierarchicalprobabilistic3dhuman_b200.distributed import shard_range, GatherBuffers, SymmPush
 
 
 def test_shard_range_partitions_exactly():
@@ -46,6 +46,11 @@ def _worker(rank, world, port, q):
                 ok &= bool(torch.equal(t[i], exp))
         # the local slice aliases the gather buffer (no pack/copy)
         ok &= gb.local("betas").data_ptr() == gb.full["betas"][rank * B:].data_ptr()
+        # copy-engine transport: without CUDA symmetric memory every rank must agree on the fallback (ok == False on all
+        # ranks, a plain buffer of the requested shape, push() a no-op) instead of dead-locking or diverging
+        sp = SymmPush((2, world, 3, 5), "cpu", rank, world)
+        ok &= (not sp.ok) and tuple(sp.full.shape) == (2, world, 3, 5) and sp.error is not None
+        sp.push(lambda buf: buf[0, rank], None)
         q.put((rank, ok, gb.bytes_received_per_rank(["vertices"])))
     finally:
         dist.destroy_process_group()

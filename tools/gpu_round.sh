@@ -9,6 +9,6 @@ tail -3 $OUT/${TAG}_pytest.log
 timeout 600 python bench.py --steps 10 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?"
 cat $OUT/${TAG}_bench.json
 timeout 300 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__throughput.avg.pct_of_peak_sustained_elapsed --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv python bench.py --profile --steps 1 > $OUT/${TAG}_ncu_launch.log 2>&1; echo "ncu launches rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'lbs_tile|mf_sample|proxy_rep|stem2' -c 8 -o $OUT/${TAG}_full python bench.py --profile --steps 1 > $OUT/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'lbs_tile|mf_sample|stem2|vertex_unc|blend_tc' -c 12 -o $OUT/${TAG}_full python bench.py --profile --steps 1 > $OUT/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ncu -i $OUT/${TAG}_full.ncu-rep --page raw --csv > $OUT/${TAG}_full_raw.csv 2>/dev/null
 ls -la $OUT
