@@ -182,6 +182,25 @@ def synthetic_images(batch, seed=0, size=256):
     return rgb, j2d, vis
 
 
+def synthetic_crop_inputs(batch, seed=0, height=384, width=288):
+    """Inputs of the crop / resample step in front of the proxy representation (reference predict/...:73-93,
+    SURVEY.md §8f rank 3): an HRNet-sized RGB image (B,3,height,width) in [0,1], (B,17,2) joints in it, bounding-box
+    centres (B,2) as (vertical, horizontal), heights (B,), widths (B,) -- the first box is the whole image like the
+    predict path's, the others are arbitrary (also partly outside the image)."""
+    rs = np.random.RandomState(seed)
+    rgb = rs.uniform(0, 1, size=(batch, 3, height // 8, width // 8)).astype(np.float32)
+    rgb = np.repeat(np.repeat(rgb, 8, axis=2), 8, axis=3)
+    rgb = np.clip(rgb + rs.normal(0, 0.05, size=rgb.shape).astype(np.float32), 0.0, 1.0)
+    j2d = (rs.uniform(0, 1, size=(batch, 17, 2)) * np.array([width, height])).astype(np.float32)
+    centres = np.stack([rs.uniform(0.3 * height, 0.7 * height, batch), rs.uniform(0.3 * width, 0.7 * width, batch)], axis=1)
+    heights = rs.uniform(0.3 * height, 1.1 * height, batch)
+    widths = rs.uniform(0.3 * width, 1.1 * width, batch)
+    centres[0] = (height * 0.5, width * 0.5)
+    heights[0] = height
+    widths[0] = height
+    return rgb, j2d, centres.astype(np.float32), heights.astype(np.float32), widths.astype(np.float32)
+
+
 def randomise_bn_stats(module, seed=0):
     """running_mean~N(0,0.1), running_var~U(0.5,1.5), gamma~U(0.5,1.5), beta~N(0,0.1) on every
     BatchNorm2d of a torch module, from a numpy stream (torch-version independent)."""

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-from oracle import reference_import, net_oracle, sampler_oracle, proxy_oracle   # noqa: E402
+from oracle import reference_import, net_oracle, sampler_oracle, proxy_oracle, crop_oracle   # noqa: E402
 from hierarchicalprobabilistic3dhuman_b200 import synthetic as syn   # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
@@ -130,6 +130,29 @@ def main():
     with torch.no_grad():
         store["feats"] = model.image_encoder(proxy).numpy()
     np.savez_compressed(os.path.join(GOLD, "proxy_b2.npz"), **store)
+    # ---- crop / affine resample and HRNet key-point arg-max: the reference's own functions
+    with contextlib.redirect_stdout(io.StringIO()):
+        from utils.image_utils import batch_crop_pytorch_affine
+        from predict.predict_hrnet import get_kp_locations_confs_from_heatmaps
+    crgb, cj2d, cc, ch, cw = (torch.from_numpy(a) for a in syn.synthetic_crop_inputs(3, seed=8))
+    store = {"crop_seed": 8, "rgb_checksum": checksum(crgb)}
+    for tag, scale in (("s10", 1.0), ("s12", 1.2)):            # predict/...:93 uses 1.0, the function's default is 1.2
+        r_ = batch_crop_pytorch_affine(input_wh=(288, 384), output_wh=(256, 256), num_to_crop=3, device="cpu", joints2D=cj2d,
+                                       rgb=crgb, bbox_centres=cc.clone(), bbox_heights=ch.clone(), bbox_widths=cw.clone(),
+                                       orig_scale_factor=scale)
+        o_ = crop_oracle.batch_crop_affine((288, 384), (256, 256), cj2d, crgb, cc, ch, cw, scale)
+        assert torch.equal(r_["joints2D"], o_["joints2D"]) and torch.equal(r_["rgb"], o_["rgb"]), tag
+        store[f"joints2D_{tag}"] = r_["joints2D"].numpy()
+        store[f"rgb_rows_{tag}"] = r_["rgb"][:, :, ::31, :].numpy()          # every 31st row (9 rows), exact
+        store[f"rgb_checksum_{tag}"] = checksum(r_["rgb"])
+    rs = np.random.RandomState(4)
+    hm = torch.from_numpy(rs.normal(size=(2, 17, 96, 72)).astype(np.float32))
+    hm[0, 3] = -1.0                                                          # never positive: key point zeroed
+    kps, confs = get_kp_locations_confs_from_heatmaps(hm)
+    k2, c2 = crop_oracle.keypoints_from_heatmaps(hm)
+    assert torch.equal(kps, k2) and torch.equal(confs, c2)
+    store["hrnet_kps"], store["hrnet_confs"] = kps.numpy(), confs.numpy()
+    np.savez_compressed(os.path.join(GOLD, "crop_b3.npz"), **store)
     print("golden fixtures written to", os.path.normpath(GOLD))
     for f in sorted(os.listdir(GOLD)):
         print(" ", f, os.path.getsize(os.path.join(GOLD, f)))

@@ -124,3 +124,27 @@ def test_proxy_oracle_small_known_answers():
     # heat-map: peak 1 at an integer joint, (u, v) = (column, row)
     h = proxy_oracle.joints2d_to_heatmaps(torch.tensor([[[5.0, 9.0]]]), 16, 4)
     assert h[0, 0, 9, 5] == 1.0 and h[0, 0].argmax().item() == 9 * 16 + 5
+
+
+def test_crop_oracle_matches_reference_golden():
+    """Crop / affine resample and HRNet key-point arg-max (groundwork: oracle only) vs outputs of
+    the reference's own batch_crop_pytorch_affine / get_kp_locations_confs_from_heatmaps: bit-identical."""
+    from oracle import crop_oracle
+    g = load_golden("crop_b3")
+    rgb, j2d, c, h, w = (torch.from_numpy(a) for a in syn.synthetic_crop_inputs(3, seed=int(g["crop_seed"])))
+    np.testing.assert_allclose(_checksum(rgb), g["rgb_checksum"], rtol=1e-12)
+    for tag, scale in (("s10", 1.0), ("s12", 1.2)):
+        o = crop_oracle.batch_crop_affine((288, 384), (256, 256), j2d, rgb, c, h, w, scale)
+        assert np.array_equal(o["joints2D"].numpy(), g[f"joints2D_{tag}"]), tag
+        assert np.array_equal(o["rgb"][:, :, ::31, :].numpy(), g[f"rgb_rows_{tag}"]), tag
+        np.testing.assert_allclose(_checksum(o["rgb"]), g[f"rgb_checksum_{tag}"], rtol=1e-12)
+    # the predict path's call (whole image as the box, scale 1.0) is a pure resize: joints scale by 256/384 about the centre
+    o = crop_oracle.batch_crop_affine((288, 384), (256, 256), j2d[:1], None, c[:1], h[:1], w[:1], 1.0)
+    exp = (j2d[:1] - torch.tensor([144.0, 192.0])) * (256.0 / 384.0) + 128.0
+    assert (o["joints2D"] - exp).abs().max() < 1e-4
+    rs = np.random.RandomState(4)
+    hm = torch.from_numpy(rs.normal(size=(2, 17, 96, 72)).astype(np.float32))
+    hm[0, 3] = -1.0
+    kps, confs = crop_oracle.keypoints_from_heatmaps(hm)
+    assert np.array_equal(kps.numpy(), g["hrnet_kps"]) and np.array_equal(confs.numpy(), g["hrnet_confs"])
+    assert kps[0, 3].tolist() == [0.0, 0.0] and confs[0, 3] == -1.0
