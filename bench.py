@@ -55,6 +55,11 @@ def parse():
     return ap.parse_args()
 
 
+def workload_name(B, N):
+    return (f"BASELINE configs[1]/[3] at the metric's batch: {B} images/GPU x N={N} samples, 18x256x256 proxy rep, "
+            f"full hot path (encoder+head+sampler+SMPL on {B * N} meshes/GPU)")
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -181,9 +186,10 @@ def main_reference(args):
     line = {"metric": "images/sec (B=256, N_samples=100)", "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"1xB200 config: batch 256/GPU, N_samples=100, 18x256x256 proxy rep; reference arm runs a bounded "
-                                   f"sample of {args.ref_batch} images/step/worker on all host cores", "encoder": "ResNet-18",
-                       "smpl": "synthetic SMPL-shaped model (licence-gated file absent)"},
+            "config": {"workload": workload_name(args.batch, args.samples),
+                       "reference_sample": f"bounded sample of the workload: {args.ref_batch} images x N={args.samples} samples per step per "
+                                           f"worker process on all host cores (the same per-image work as the GPU arm)",
+                       "encoder_mode": "fp32 torch CPU", "smpl": "synthetic SMPL-shaped model (licence-gated file absent)"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -437,8 +443,7 @@ def main_hp3d(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f16 (encoder, fp32 accumulate) + f32 (head, sampler, SMPL; blend = 3x fp16-split tensor-core)" if args.encoder_mode == "fast" else "f32",
                 "data": "synthetic",
-                "config": {"workload": f"BASELINE configs[1]/[3] at the metric's batch: {B} images/GPU x N={N} samples, 18x256x256 proxy rep, "
-                                       f"full hot path (encoder+head+sampler+SMPL on {B * N} meshes/GPU)",
+                "config": {"workload": workload_name(B, N),
                            "encoder_mode": args.encoder_mode, "gather": args.gather if world > 1 else "none", "gather_transport": transport, "gather_verified": gather_ok,
                            "persistent_kernel_ctas": int(os.environ.get("HP3D_SM_LIMIT", "0")) or "all SMs",
                            "l2": "inputs (1.2 GB/step) and outputs (2.1 GB/step) exceed the 126 MB L2; no explicit flush",
