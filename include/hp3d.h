@@ -109,6 +109,19 @@ int hp3d_proxy_rep(const float* rgb, const float* joints2d, const unsigned char*
 int hp3d_joints2d_heatmap_argmax(const float* joints2d, const unsigned char* visibility, int B, int K, int img_wh,
                                  float std, float eps, float* joints2d_px, int32_t* vis_out, void* stream);
 
+/* ---------------------------------------------------------------- crop / resample in front of it
+ * replaces: utils/image_utils.py:234-378 (batch_crop_pytorch_affine) for a GIVEN bounding box (predict/...:84-93):
+ * rgb [B*C*H*W] -> rgb_out [B*C*out_h*out_w] by F.affine_grid + bilinear F.grid_sample (align_corners=False, zeros),
+ * joints2d [B*K*2] -> joints_out by the forward affine; either pair may be NULL. bbox_centres [B*2] as (vertical,
+ * horizontal), bbox_heights / bbox_widths [B]; scale_factor = orig_scale_factor. Arithmetic: csrc/crop_math.h, verified
+ * on the host bit for bit; the kernels have not yet run on hardware. */
+int hp3d_crop_affine(const float* rgb, const float* joints2d, int B, int C, int H, int W, int K, const float* bbox_centres,
+                     const float* bbox_heights, const float* bbox_widths, float scale_factor, int out_w, int out_h,
+                     float* rgb_out, float* joints_out, void* stream);
+/* replaces: predict/predict_hrnet.py:7-30 (get_kp_locations_confs_from_heatmaps): heatmaps [B*K*h*w] -> keypoints
+ * [B*K*2] (x, y of the arg-max; 0 where the maximum is not positive), confs [B*K] (the maxima). */
+int hp3d_heatmap_keypoints(const float* heatmaps, int B, int K, int h, int w, float* keypoints, float* confs, void* stream);
+
 /* ---------------------------------------------------------------- matrix-Fisher sampler
  * replaces: utils/sampling_utils.py:74-143 (pose_matrix_fisher_sampling_torch) incl. :10-71
  * (bingham_sampling_for_matrix_fisher_torch) and utils/rigid_transform_utils.py:113-133.
