@@ -7,7 +7,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libhp3d.so")
 HOST_SHIM_PATH = os.path.join(PKG_DIR, "libhp3d_hostshim.so")
-SOURCES = ["api.cu", "smpl.cu", "mf_sampler.cu", "mf_head.cu", "encoder.cu", "conv_tc.cu", "gemm_tc.cu", "rank.cu", "proxy.cu", "crop.cu"]
+SOURCES = ["api.cu", "smpl.cu", "mf_sampler.cu", "mf_head.cu", "encoder.cu", "conv_tc.cu", "gemm_tc.cu", "rank.cu", "proxy.cu", "crop.cu", "mf_norm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -38,7 +38,7 @@ def build(force=False, verbose=False):
         if verbose:
             print(r.stderr)
     shim_src = os.path.join(CSRC, "host_shim.cpp")
-    if force or not _newer(HOST_SHIM_PATH, [shim_src, os.path.join(CSRC, "svd3.h"), os.path.join(CSRC, "crop_math.h")]):
+    if force or not _newer(HOST_SHIM_PATH, [shim_src, os.path.join(CSRC, "svd3.h"), os.path.join(CSRC, "crop_math.h"), os.path.join(CSRC, "mf_norm_math.h")]):
         r = subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", HOST_SHIM_PATH, shim_src],
                            capture_output=True, text=True)
         if r.returncode != 0:

@@ -27,3 +27,17 @@ extern "C" void hp3d_host_crop(const float* rgb, const float* joints, int B, int
       }
   }
 }
+
+// matrix-Fisher normalising constant (csrc/mf_norm_math.h) on the host, nodes summed sequentially
+#include "mf_norm_math.h"
+extern "C" void hp3d_host_mf_log_norm(const float* S, long n, float* log_c, float* dlogc_ds) {
+  for (long r = 0; r < n; ++r) {
+    float sum[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < hp3d::MF_NORM_TRAPS; ++i) {
+      float t[4];
+      hp3d::mf_norm_node_terms(i, S[3 * r], S[3 * r + 1], S[3 * r + 2], t);
+      for (int q = 0; q < 4; ++q) sum[q] += t[q];
+    }
+    hp3d::mf_norm_finish(sum, S[3 * r], S[3 * r + 1], S[3 * r + 2], log_c + r, dlogc_ds ? dlogc_ds + 3 * r : nullptr);
+  }
+}

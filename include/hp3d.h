@@ -134,6 +134,12 @@ int hp3d_mf_sample(const float* U, const float* S, const float* V, int B, int J,
                    uint64_t seed, uint64_t offset, const float* eps, const float* w, int oversampling,
                    float* R_out, unsigned long long* stats, void* stream);
 
+/* matrix-Fisher normalising constant, replaces losses/matrix_fisher_loss.py:134-192
+ * (LogMFNormConstant.forward / backward): S_proper [n*3] proper singular values (s1 >= s2 >= |s3|) -> log_c [n] =
+ * log c(S), dlogc_ds [n*3] = d log c / d s_k (may be NULL). 512-node trapezoid rule over scaled Bessel-I0 products.
+ * Arithmetic: csrc/mf_norm_math.h, verified on the host; the kernel has not yet run on hardware. */
+int hp3d_mf_log_norm_constant(const float* S_proper, int n, float* log_c, float* dlogc_ds, void* stream);
+
 /* ---------------------------------------------------------------- distribution head
  * replaces: models/poseMF_shapeGaussian_net.py:95-160 (everything after the encoder). */
 typedef struct hp3d_head hp3d_head;

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-from oracle import reference_import, net_oracle, sampler_oracle, proxy_oracle, crop_oracle   # noqa: E402
+from oracle import reference_import, net_oracle, sampler_oracle, proxy_oracle, crop_oracle, mf_loss_oracle   # noqa: E402
 from hierarchicalprobabilistic3dhuman_b200 import synthetic as syn   # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
@@ -153,6 +153,19 @@ def main():
     assert torch.equal(kps, k2) and torch.equal(confs, c2)
     store["hrnet_kps"], store["hrnet_confs"] = kps.numpy(), confs.numpy()
     np.savez_compressed(os.path.join(GOLD, "crop_b3.npz"), **store)
+    # ---- matrix-Fisher normalising constant and its gradient: the reference's LogMFNormConstant
+    with contextlib.redirect_stdout(io.StringIO()):
+        from losses.matrix_fisher_loss import LogMFNormConstant
+    rs = np.random.RandomState(6)
+    Sn = np.exp(rs.uniform(np.log(1e-2), np.log(5e2), size=(600, 3))).astype(np.float32)
+    Sn = -np.sort(-Sn, axis=1)
+    Sn[::3, 2] *= -1.0                                                       # proper s3 is negative when det(U V^T) = -1
+    St = torch.from_numpy(Sn).requires_grad_(True)
+    lc = LogMFNormConstant.apply(St)
+    lc.sum().backward()
+    lo, go = mf_loss_oracle.log_mf_norm_constant(torch.from_numpy(Sn))
+    assert torch.equal(lo, lc.detach()) and torch.equal(go, St.grad)
+    np.savez_compressed(os.path.join(GOLD, "mf_norm.npz"), S=Sn, log_c=lc.detach().numpy(), dlogc_ds=St.grad.numpy())
     print("golden fixtures written to", os.path.normpath(GOLD))
     for f in sorted(os.listdir(GOLD)):
         print(" ", f, os.path.getsize(os.path.join(GOLD, f)))
