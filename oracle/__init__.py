@@ -10,7 +10,8 @@ Parity status:
   in the build container, checks these restatements against it and writes the small golden
   fixtures under tests/golden/ that the GPU box replays.
 * proxy-representation generation (Canny edges, joint heat-maps, heat-map arg-max), sample-ranking helpers and the crop /
-  affine resample + HRNet key-point arg-max (`proxy_oracle.py`, `crop_oracle.py`, `sampler_oracle.py`): PINNED -- bit-identical
+  affine resample + HRNet key-point arg-max, and the matrix-Fisher normalising constant (`proxy_oracle.py`, `crop_oracle.py`,
+  `sampler_oracle.py`, `mf_loss_oracle.py`): PINNED -- bit-identical
   to the imported reference functions on the fixtures (`oracle/make_golden.py` asserts it).
 * SMPL forward (smplx 0.1.26 `lbs`, third-party, absent from /root/reference and not installable):
   PARITY UNPINNED -- restated from the published algorithm; pinned only
