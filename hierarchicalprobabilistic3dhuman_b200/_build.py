@@ -31,12 +31,29 @@ def build(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     if force or not _newer(LIB_PATH, _deps()):
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + srcs
-        r = subprocess.run(cmd, capture_output=True, text=True)
+        # one nvcc process per translation unit, in parallel (no relocatable device code: every kernel is self-contained),
+        # then a link step; objects live in build/ (git-ignored)
+        from concurrent.futures import ThreadPoolExecutor
+        obj_dir = os.path.join(PKG_DIR, "build")
+        os.makedirs(obj_dir, exist_ok=True)
+        flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+        def compile_one(src):
+            obj = os.path.join(obj_dir, os.path.basename(src) + ".o")
+            r = subprocess.run([nvcc] + flags + ["-c", "-o", obj, src], capture_output=True, text=True)
+            return obj, r
+
+        with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as ex:
+            results = list(ex.map(compile_one, srcs))
+        for obj, r in results:
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+            if verbose:
+                print(r.stderr)
+        r = subprocess.run([nvcc, "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH]
+                           + [obj for obj, _ in results], capture_output=True, text=True)
         if r.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-        if verbose:
-            print(r.stderr)
+            raise RuntimeError("nvcc link failed:\n" + r.stdout + r.stderr)
     shim_src = os.path.join(CSRC, "host_shim.cpp")
     if force or not _newer(HOST_SHIM_PATH, [shim_src, os.path.join(CSRC, "svd3.h"), os.path.join(CSRC, "crop_math.h"), os.path.join(CSRC, "mf_norm_math.h")]):
         r = subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", HOST_SHIM_PATH, shim_src],
