@@ -48,3 +48,22 @@ def test_known_answers(built_lib):
         assert np.abs(fd - grad[:, k])[:2].max() < 2e-3, (k, fd, grad[:, k])
     # concentrated distributions: E[R] -> identity, i.e. every d log c / d s_k -> 1
     assert (grad[2] > 0.98).all() and (grad[2] < 1.0).all()
+
+
+def test_sampler_oracle_mean_matches_normaliser_gradient(built_lib):
+    """Cross-check of two independently restated pieces of the reference: for a matrix-Fisher distribution with
+    F = U diag(S) V^T, E[R] = U_p diag(d log c / d s) V_p^T. The Monte-Carlo mean of the (reference-pinned) rejection
+    sampler must agree with the (reference-pinned) normalising-constant gradient, including an improper factor pair."""
+    from oracle import sampler_oracle
+    S = torch.tensor([[[5.0, 3.0, 1.0], [0.3, 0.2, 0.1], [20.0, 15.0, 10.0], [4.0, 2.0, 0.5]]])
+    U = torch.eye(3).expand(1, 4, 3, 3).clone()
+    V = U.clone()
+    U[0, 3, :, 2] *= -1.0                                    # det U = -1: proper s3 = -0.5
+    N = 20000
+    g = torch.Generator().manual_seed(3)
+    R = sampler_oracle.sample(U, S, V, N, generator=g)       # (1, N, 4, 3, 3)
+    Up, Sp, Vp = sampler_oracle.proper_usv(U, S, V)
+    _, grad = host_log_norm(built_lib, Sp[0].numpy())
+    ER = torch.einsum("jab,jb,jcb->jac", Up[0], torch.from_numpy(grad), Vp[0])
+    err = (R[0].mean(0) - ER).abs().max().item()
+    assert err < 4.0 / np.sqrt(N), err
