@@ -49,6 +49,21 @@ int upload(T** dptr, const T* host, size_t n) {
   return 0;
 }
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory. The attribute is per DEVICE (context), so the "already done"
+// cache is a bit per device ordinal, not a process-wide flag: one process may drive several GPUs (handles and workspaces
+// are keyed by device on the Python side). A lost update under a race only repeats the (idempotent) call.
+#define HP3D_SMEM_OPT_IN(kernel, bytes)                                                                        \
+  do {                                                                                                         \
+    static unsigned long long done__ = 0ull;                                                                   \
+    int dev__ = 0;                                                                                             \
+    HP3D_CUDA(cudaGetDevice(&dev__));                                                                          \
+    const unsigned long long bit__ = 1ull << (dev__ & 63);                                                     \
+    if (!(__atomic_load_n(&done__, __ATOMIC_RELAXED) & bit__)) {                                               \
+      HP3D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));      \
+      __atomic_fetch_or(&done__, bit__, __ATOMIC_RELAXED);                                                     \
+    }                                                                                                          \
+  } while (0)
+
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // CTAs a persistent one-CTA-per-SM kernel may launch: the SM count, or HP3D_SM_LIMIT if set lower (multi-GPU runs leave a
 // few SMs to the NCCL all-gather kernels, which otherwise cannot start until a whole persistent kernel has drained and

@@ -1,11 +1,11 @@
 // ResNet-18 proxy-representation encoder for sm_100a (eval-mode BatchNorm folded into the convs).
 //
 // Replaces reference models/resnet.py:202-217 (+ BasicBlock.forward :62-78) for resnet18(18).
-// Two arithmetic modes behind one handle:
-//   HP3D_ENC_PARITY  fp32 NHWC activations, fp32 CUDA-core implicit GEMM (this file) -- the mode the
-//                    <=1e-4 end-to-end parity contract is checked in;
-//   HP3D_ENC_FAST    fp16 NHWC activations, tcgen05 tensor-core implicit GEMM with fp32 accumulation
-//                    in TMEM (conv_tc.cu) -- the throughput mode, reported with its own tolerance.
+// Three arithmetic modes behind one handle:
+//   HP3D_ENC_SPLIT   tcgen05 tensor-core implicit GEMM on fp16 hi/lo pairs, three products per k-block accumulated in
+//                    fp32 TMEM (conv_tc.cu) -- the default: meets the <=1e-4 contract on the tensor cores;
+//   HP3D_ENC_FAST    single fp16 product per k-block (conv_tc.cu) -- opt-in, ~3e-4 on the features;
+//   HP3D_ENC_PARITY  fp32 NHWC activations, fp32 CUDA-core implicit GEMM (this file) -- the plain-fp32 cross-check.
 // Layer plan (18x256x256 input): stem 7x7/2 -> maxpool 3x3/2 -> 4 stages x 2 BasicBlocks -> global
 // average pool -> (B,512). Layout in HBM: activations NHWC (channels innermost, stem input padded
 // 18 -> 20/32 channels), weights [kh][kw][cin][cout] so both GEMM operands are contiguous along K/N.
@@ -203,14 +203,14 @@ static int make_layer(const hp3d_conv_bn& c, float eps, int cin_pad, ConvLayer& 
 
 extern "C" int hp3d_encoder_create(const hp3d_encoder_weights* w, int mode, hp3d_encoder** out) {
   HP3D_ARG(w && out, "null argument");
-  HP3D_ARG(mode == HP3D_ENC_PARITY || mode == HP3D_ENC_FAST, "unknown mode");
+  HP3D_ARG(mode == HP3D_ENC_PARITY || mode == HP3D_ENC_FAST || mode == HP3D_ENC_SPLIT, "unknown mode");
   HP3D_ARG(w->stem.cin == 18 && w->stem.cout == 64 && w->stem.k == 7 && w->stem.stride == 2 && w->stem.pad == 3,
            "stem must be 7x7/2 pad 3, 18->64");
   hp3d_encoder* h = new hp3d_encoder();
   h->mode = mode;
   int rc = 0;
-  if (mode == HP3D_ENC_FAST) {
-    rc = encoder_tc_create(w, &h->tc);
+  if (mode != HP3D_ENC_PARITY) {
+    rc = encoder_tc_create(w, mode == HP3D_ENC_SPLIT, &h->tc);
   } else {
     rc = make_layer(w->stem, w->bn_eps, 20, h->stem);
     const int planes[4] = {64, 128, 256, 512};
@@ -261,7 +261,7 @@ static size_t enc_ws_parity(int B, int H, int W) {
 
 extern "C" size_t hp3d_encoder_workspace_bytes(const hp3d_encoder* h, int B, int H, int W) {
   if (!h || B <= 0) return 0;
-  if (h->mode == HP3D_ENC_FAST) return encoder_tc_workspace_bytes(h->tc, B, H, W);
+  if (h->mode != HP3D_ENC_PARITY) return encoder_tc_workspace_bytes(h->tc, B, H, W);
   return enc_ws_parity(B, H, W);
 }
 
@@ -287,7 +287,7 @@ extern "C" int hp3d_encoder_forward_image(const hp3d_encoder* h, const float* rg
                                           int gaussian_size, float threshold, int nms, float heat_std, float* feats,
                                           void* workspace, size_t workspace_bytes, void* stream_) {
   HP3D_ARG(h && rgb && joints2d && feats && workspace, "null argument");
-  HP3D_ARG(h->mode == HP3D_ENC_FAST, "fused image input needs HP3D_ENC_FAST (parity mode: hp3d_proxy_rep + hp3d_encoder_forward)");
+  HP3D_ARG(h->mode != HP3D_ENC_PARITY, "fused image input needs a tensor-core handle (HP3D_ENC_SPLIT / HP3D_ENC_FAST); HP3D_ENC_PARITY: hp3d_proxy_rep + hp3d_encoder_forward");
   HP3D_ARG(B > 0 && img_wh == 256, "256x256 proxy representations (DATA.PROXY_REP_SIZE)");
   HP3D_ARG(workspace_bytes >= hp3d_encoder_workspace_bytes(h, B, img_wh, img_wh), "workspace too small");
   const ImageInput im = {rgb, joints2d, visibility, gaussian_std, gaussian_size, threshold, nms, heat_std};
@@ -298,7 +298,7 @@ extern "C" int hp3d_encoder_forward_argmax(const hp3d_encoder* h, const float* x
                                            void* workspace, size_t workspace_bytes, float eps, float* joints2d_px,
                                            int32_t* vis, void* stream_) {
   HP3D_ARG(h && x && feats && workspace && joints2d_px && vis, "null argument");
-  if (h->mode == HP3D_ENC_FAST) {
+  if (h->mode != HP3D_ENC_PARITY) {
     HP3D_ARG(B > 0 && H >= 32 && W >= 32 && H % 32 == 0 && W % 32 == 0, "H and W must be multiples of 32");
     HP3D_ARG(workspace_bytes >= hp3d_encoder_workspace_bytes(h, B, H, W), "workspace too small");
     const ArgmaxOut am = {eps, joints2d_px, vis};
@@ -315,7 +315,7 @@ extern "C" int hp3d_encoder_forward_taps(const hp3d_encoder* h, const float* x, 
   HP3D_ARG(B > 0 && H >= 32 && W >= 32 && H % 32 == 0 && W % 32 == 0, "H and W must be multiples of 32");
   HP3D_ARG(workspace_bytes >= hp3d_encoder_workspace_bytes(h, B, H, W), "workspace too small");
   cudaStream_t s = (cudaStream_t)stream_;
-  if (h->mode == HP3D_ENC_FAST) return encoder_tc_forward(h->tc, x, B, H, W, feats, workspace, workspace_bytes, taps, s);
+  if (h->mode != HP3D_ENC_PARITY) return encoder_tc_forward(h->tc, x, B, H, W, feats, workspace, workspace_bytes, taps, s);
   char* ws = (char*)workspace;
   float* xin = (float*)ws; ws += align_up((size_t)B * H * W * 20 * 4, 256);
   float* stem = (float*)ws; ws += align_up((size_t)B * (H / 2) * (W / 2) * 64 * 4, 256);

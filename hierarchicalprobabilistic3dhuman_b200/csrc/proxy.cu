@@ -46,6 +46,7 @@ struct ProxyArgs {
   const float* joints2d; const unsigned char* vis; int K; float std;   // optional fused heat-maps
   float* heat; long long heat_stride;                       // (B,K,H,W)-like destination, images heat_stride apart
   __half* nhwc32;                                            // optional fp16 NHWC records of 32 channels (edge | K heat | 0)
+  int nhwc_split;                                            // 1: 64-channel hi/lo records of the split stem (conv_tc.cu) instead
 };
 
 __device__ __forceinline__ float heat_value(float row, float col, float u, float v, float std) {
@@ -163,7 +164,28 @@ __global__ void __launch_bounds__(256) proxy_rep_kernel(const ProxyArgs a) {
         a.heat[(size_t)b * a.heat_stride + (size_t)k * HW + pix] =
             __fmul_rn(heat_value((float)y, (float)x, sj[2 * k], sj[2 * k + 1], a.std), svis[k]);
     }
-    if (a.nhwc32) {
+    if (a.nhwc32 && a.nhwc_split) {
+      // [A_hi c0..15 | A_hi c0..15 | A_lo c0..15 | A_hi c16,17 | A_hi c16,17 | A_lo c16,17 | 0 x 10]  (stem2_kernel<true>)
+      __half2 h[9], l[9];
+      float prev = edge;
+#pragma unroll
+      for (int k = 0; k < 17; ++k) {                                   // channel k+1 = heat-map k
+        const float v = __fmul_rn(heat_value((float)y, (float)x, sj[2 * k], sj[2 * k + 1], a.std), svis[k]);
+        if (k & 1) prev = v;
+        else {
+          h[k >> 1] = __floats2half2_rn(prev, v);
+          const float2 f = __half22float2(h[k >> 1]);
+          l[k >> 1] = __floats2half2_rn(prev - f.x, v - f.y);
+        }
+      }
+      uint4* dst = reinterpret_cast<uint4*>(a.nhwc32 + ((size_t)b * HW + pix) * 64);
+      dst[0] = *reinterpret_cast<const uint4*>(&h[0]); dst[1] = *reinterpret_cast<const uint4*>(&h[4]);
+      dst[2] = dst[0]; dst[3] = dst[1];
+      dst[4] = *reinterpret_cast<const uint4*>(&l[0]); dst[5] = *reinterpret_cast<const uint4*>(&l[4]);
+      const __half2 t[4] = {h[8], h[8], l[8], __float2half2_rn(0.f)};
+      dst[6] = *reinterpret_cast<const uint4*>(&t[0]);
+      dst[7] = make_uint4(0u, 0u, 0u, 0u);
+    } else if (a.nhwc32) {
       __half2 h[16];
       float prev = edge;
 #pragma unroll
@@ -283,15 +305,16 @@ extern "C" int hp3d_proxy_rep(const float* rgb, const float* joints2d, const uns
 }
 
 namespace hp3d {
-// fused producer of the tensor-core encoder's input (conv_tc.cu): fp16 NHWC records of 32 channels
-int proxy_rep_nhwc32_f16(const float* rgb, const float* joints2d, const unsigned char* visibility, int B, int img_wh,
-                         float gaussian_std, int gaussian_size, float threshold, int nms, float heat_std, void* nhwc32,
-                         cudaStream_t stream) {
+// fused producer of the tensor-core encoder's input (conv_tc.cu): fp16 NHWC records of 32 channels (fast mode) or the
+// split stem's 64-channel hi/lo records (split = 1)
+int proxy_rep_nhwc_f16(const float* rgb, const float* joints2d, const unsigned char* visibility, int B, int img_wh,
+                       float gaussian_std, int gaussian_size, float threshold, int nms, float heat_std, void* nhwc32,
+                       int split, cudaStream_t stream) {
   ProxyArgs a = {};
   a.img = rgb; a.C = 3; a.H = img_wh; a.W = img_wh; a.threshold = threshold; a.nms = nms ? 1 : 0;
   if (fill_gauss(a, gaussian_std, gaussian_size)) return -1;
   a.joints2d = joints2d; a.vis = visibility; a.K = 17; a.std = heat_std;
-  a.nhwc32 = (__half*)nhwc32;
+  a.nhwc32 = (__half*)nhwc32; a.nhwc_split = split;
   proxy_rep_kernel<<<dim3(cdiv(img_wh, CT), cdiv(img_wh, CT), B), 256, 0, stream>>>(a);
   return launch_status("proxy_rep_kernel");
 }

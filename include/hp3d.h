@@ -180,8 +180,9 @@ typedef struct {
   hp3d_conv_bn down[4];                 /* 1x1 s2 downsample of layers 2..4 (down[0] unused, w=NULL) */
   float bn_eps;
 } hp3d_encoder_weights;
-#define HP3D_ENC_PARITY 0   /* fp32 CUDA-core implicit GEMM (<=1e-4 end-to-end contract)            */
-#define HP3D_ENC_FAST 1     /* fp16 operands, fp32 accumulate, tcgen05 tensor-core implicit GEMM   */
+#define HP3D_ENC_PARITY 0   /* fp32 CUDA-core implicit GEMM (plain-fp32 cross-check of the contract)                      */
+#define HP3D_ENC_FAST 1     /* fp16 operands, fp32 accumulate, tcgen05 implicit GEMM, ONE product: ~3e-4 on the features  */
+#define HP3D_ENC_SPLIT 2    /* tcgen05 implicit GEMM on fp16 hi/lo pairs, three products in fp32 TMEM: <=1e-4 (default)    */
 int hp3d_encoder_create(const hp3d_encoder_weights* w, int mode, hp3d_encoder** out);
 void hp3d_encoder_destroy(hp3d_encoder* h);
 size_t hp3d_encoder_workspace_bytes(const hp3d_encoder* h, int B, int H, int W);
@@ -194,7 +195,7 @@ int hp3d_encoder_forward(const hp3d_encoder* h, const float* x_nchw, int B, int 
 int hp3d_encoder_forward_argmax(const hp3d_encoder* h, const float* x_nchw, int B, int H, int W, float* feats,
                                 void* workspace, size_t workspace_bytes, float eps, float* joints2d_px, int32_t* vis,
                                 void* stream);
-/* image-space entry (HP3D_ENC_FAST handles only): rgb [B*3*256*256] in [0,1], joints2d [B*17*2], visibility [B*17]
+/* image-space entry (tensor-core handles only: HP3D_ENC_SPLIT / HP3D_ENC_FAST): rgb [B*3*256*256] in [0,1], joints2d [B*17*2], visibility [B*17]
  * bytes or NULL -> feats. The Canny + heat-map kernel writes the stem's fp16 NHWC input records directly: the fp32
  * proxy representation of predict/...:100 never exists in memory. Same workspace as hp3d_encoder_forward. */
 int hp3d_encoder_forward_image(const hp3d_encoder* h, const float* rgb, const float* joints2d,
