@@ -39,7 +39,9 @@ def parse():
     ap.add_argument("--impl", default="hp3d", choices=["hp3d", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU")
     ap.add_argument("--samples", type=int, default=100)
-    ap.add_argument("--encoder-mode", default="fast", choices=["fast", "parity"])
+    ap.add_argument("--encoder-mode", default="split", choices=["split", "fast", "parity"],
+                    help="split = tcgen05 on fp16 hi/lo pairs, 3 products (meets the 1e-4 contract; default); fast = one fp16 product "
+                         "(3e-4 on the features); parity = fp32 CUDA cores")
     ap.add_argument("--ref-batch", type=int, default=4, help="images per step of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="one warm-up + the timed steps only (for ncu): no e2e / LBS-alone / CPU legs")
@@ -432,6 +434,23 @@ def main_hp3d(args):
     pk, pk_kind = peaks()
     achieved = LBS_BYTES_PER_MESH * M / (lbs_ms * 1e-3) / 1e9
 
+    # ---- opt-in single-product encoder, reported BESIDE the headline (it misses the 1e-4 contract: 3e-4 on the features)
+    ms_fast = None
+    if world == 1 and args.encoder_mode != "fast":
+        net_f = hp.PoseMFShapeGaussianNet(syn.SMPL_PARENTS.tolist(), cfg(), encoder_mode="fast")
+        net_f.load_state_dict(syn.synthetic_state_dict(0))
+        pipe.net = net_f.to(dev).eval()
+        for _ in range(3):
+            step(x_dev)
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            step(x_dev)
+        e1.record()
+        sync_all()
+        ms_fast = e0.elapsed_time(e1) / args.steps
+        pipe.net = net
+
     # max over ranks
     t = torch.tensor([ms, ms_e2e, ms_e2e_img], device=dev, dtype=torch.float64)
     if world > 1:
@@ -441,7 +460,9 @@ def main_hp3d(args):
         line = {"metric": "images/sec (B=256, N_samples=100)", "value": world * B / (ms * 1e-3), "unit": "images/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f16 (encoder, fp32 accumulate) + f32 (head, sampler, SMPL; blend = 3x fp16-split tensor-core)" if args.encoder_mode == "fast" else "f32",
+                "dtype": {"split": "f32-equivalent: encoder and blend GEMM = tcgen05 on fp16 hi/lo pairs, 3 products, fp32 accumulate (1e-4 contract met); head, sampler, LBS f32",
+                          "fast": "f16 (encoder, fp32 accumulate; 3e-4 on the features) + f32 (head, sampler, SMPL; blend = 3x fp16-split tensor-core)",
+                          "parity": "f32"}[args.encoder_mode],
                 "data": "synthetic",
                 "config": {"workload": workload_name(B, N),
                            "encoder_mode": args.encoder_mode, "gather": args.gather if world > 1 else "none", "gather_transport": transport, "gather_verified": gather_ok,
@@ -459,6 +480,9 @@ def main_hp3d(args):
                                             "heat-maps (reference predict/...:91-100) generated on the device (SURVEY.md 8f rank 2); "
                                             "NOT the metric's input contract -- reported beside `e2e`, which is"},
                 "gpu_launches": launches,
+                "encoder_fast_optin": None if ms_fast is None else {
+                    "value": world * B / (ms_fast * 1e-3), "unit": "images/s", "ms_per_step": ms_fast,
+                    "note": "same step with --encoder-mode fast (one fp16 product per k-block): 3e-4 on the features, NOT the 1e-4 contract"},
                 "clocks": clocks,
                 "roofline": {"kernel": "lbs_tile_kernel (SMPL FK + skinning + 90 joints)", "bound": "hbm", "achieved": achieved,
                              "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],

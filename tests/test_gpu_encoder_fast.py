@@ -35,7 +35,7 @@ def test_every_activation_matches_oracle(built_lib, B):
         bad = {k: v for k, v in errs.items() if not v < tol}
         assert not bad, (mode, errs)
         if mode == "split":      # the margin, not just the bar: the split path is fp32-grade (a few 1e-6)
-            assert max(errs.values()) < 2e-5, errs
+            assert max(errs.values()) < 2e-5, errs     # measured 6e-6 (profiles/r02d_split_diag_chunked.jsonl)
 
 
 def test_split_mode_is_the_default_and_meets_the_contract_end_to_end(built_lib):
