@@ -69,6 +69,24 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
+def lbs_traffic_from_profiles(grid_ctas):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the LBS launch with `grid_ctas` CTAs from the newest committed
+    `ncu --set full` summary under profiles/ (tools/ncu_summary.py export), or (None, None)."""
+    import csv, glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_summary.csv")), reverse=True):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr = rows[0]
+            ki, gi, ri, wi = hdr.index("Kernel Name"), hdr.index("Grid Size"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(rows[1][ri], 1e9)
+            for r in rows[2:]:
+                if "lbs_tile_kernel" in r[ki] and r[gi].replace(" ", "").startswith(f"({grid_ctas},"):
+                    return (float(r[ri]) + float(r[wi])) * unit, os.path.relpath(path, ROOT)
+        except Exception:
+            continue
+    return None, None
+
+
 def cfg():
     from types import SimpleNamespace as NS
     return NS(MODEL=NS(NUM_IN_CHANNELS=18, NUM_RESNET_LAYERS=18, EMBED_DIM=256, DELTA_I=True, DELTA_I_WEIGHT=1.0,
@@ -234,7 +252,7 @@ def main_hp3d(args):
     pool = torch.from_numpy(syn.synthetic_proxy_rep(16, seed=100 + rank))
     x_host = pool.repeat((B + 15) // 16, 1, 1, 1)[:B].contiguous().pin_memory()
     x_dev = x_host.to(dev)
-    torch.manual_seed(1234 + rank)
+    torch.manual_seed(1234)          # the SAME generator state on every rank: the sampler keys Philox by the global image index
 
     # gather buffers: every rank's kernels write straight into its slice (no pack/copy)
     from hierarchicalprobabilistic3dhuman_b200.distributed import GatherBuffers
@@ -266,12 +284,12 @@ def main_hp3d(args):
         g_verts = [torch.empty(VC, world if full else 1, cbv, N, 6890, 3, device=dev) for _ in range(NBUF)]
     my = rank if full else 0
     comm_stream = torch.cuda.Stream(device=dev)
-    state = {"k": 0, "pending": [None] * NBUF, "count": 0}
+    state = {"k": 0, "pending": [None] * NBUF, "count": 0, "verts": True}
 
     transport = "p2p-copy-engine (symmetric memory)" if pushers else ("nccl" if (world > 1 and full) else "none")
 
     def on_chunk(c):
-        if world > 1 and full:
+        if world > 1 and full and state["verts"]:
             gv = g_verts[state["k"]]
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
@@ -284,7 +302,7 @@ def main_hp3d(args):
 
     pipe = hp.HotPathPipeline(net, smpl, B, N, dev, rotmats_out=gb.local("rotmats"), betas_out=gb.local("betas"),
                               vertices_out=[g_verts[0][c, my] for c in range(VC)], uncertainty_out=gb.local("uncertainty"),
-                              on_vertices_chunk=on_chunk)
+                              on_vertices_chunk=on_chunk, image_offset=rank * B)
     L = _lib.lib()
     h_smpl, joints = pipe.h_smpl, pipe.joints
     verts_local = g_verts[0][0, my]
@@ -298,7 +316,7 @@ def main_hp3d(args):
 
     def gather():
         gb.all_gather()
-        if world > 1 and full:
+        if world > 1 and full and state["verts"]:
             if pushers:
                 pushers[state["k"]].fence(comm_stream)       # all ranks' pushes of this step have landed
             ev = torch.cuda.Event()
@@ -433,6 +451,53 @@ def main_hp3d(args):
     lbs_ms = e0.elapsed_time(e1) / reps
     pk, pk_kind = peaks()
     achieved = LBS_BYTES_PER_MESH * M / (lbs_ms * 1e-3) / 1e9
+    traffic, traffic_src = lbs_traffic_from_profiles((M + 7) // 8)
+
+    # ---- the tensor-core side: encoder alone (input cast + stem + pools + 19 convolutions), algorithmic and issued FLOP/s
+    for _ in range(3):
+        net.encode(x_dev)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        net.encode(x_dev)
+    e1.record()
+    torch.cuda.synchronize()
+    enc_ms = e0.elapsed_time(e1) / reps
+    ENC_FLOP = 6.279e9                       # 2 x 3,139,436,544 MAC per image
+    issued = {"split": 3 * (ENC_FLOP - 2 * 882 * 64 * 16384) + 2 * 3136 * 64 * 16384,      # 3 products; stem K 882 -> 49 taps x 64
+              "fast": (ENC_FLOP - 2 * 882 * 64 * 16384) + 2 * 1792 * 64 * 16384, "parity": ENC_FLOP}[args.encoder_mode]
+
+    # ---- N > 1: the same step gathering statistics only (no sample vertices over NVLink)
+    ms_stats = None
+    if world > 1 and full:
+        state["verts"] = False
+        finish()
+        for _ in range(3):
+            step(x_dev)
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            step(x_dev)
+        e1.record()
+        sync_all()
+        ms_stats = e0.elapsed_time(e1) / args.steps
+        state["verts"] = True
+
+    # ---- N == 1: end to end INCLUDING the sampled vertices (2.12 GB/step of D2H)
+    ms_full = None
+    if world == 1 and pipe.vertices is not None:
+        nfull = max(2, min(args.steps, 4))
+        last = pipe.run_host(x_hosts[0], return_vertices=True)
+        last[1].synchronize()
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(nfull):
+            last = pipe.run_host(x_hosts[i & 1], return_vertices=True)
+        last[1].synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_full = e0.elapsed_time(e1) / nfull
+        pipe.release_host_vertices()
 
     # ---- opt-in single-product encoder, reported BESIDE the headline (it misses the 1e-4 contract: 3e-4 on the features)
     ms_fast = None
@@ -452,10 +517,11 @@ def main_hp3d(args):
         pipe.net = net
 
     # max over ranks
-    t = torch.tensor([ms, ms_e2e, ms_e2e_img], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, ms_e2e, ms_e2e_img, ms_stats or 0.0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_e2e_img = t.tolist()
+    ms, ms_e2e, ms_e2e_img, ms_stats_max = t.tolist()
+    ms_stats = ms_stats_max if ms_stats is not None else None
     if rank == 0:
         line = {"metric": "images/sec (B=256, N_samples=100)", "value": world * B / (ms * 1e-3), "unit": "images/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
@@ -486,8 +552,25 @@ def main_hp3d(args):
                 "clocks": clocks,
                 "roofline": {"kernel": "lbs_tile_kernel (SMPL FK + skinning + 90 joints)", "bound": "hbm", "achieved": achieved,
                              "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                             "traffic": 4.2867e9 if M == 25600 else None, "traffic_source": "profiles/r01p_ncu_full_summary.csv (ncu --set full: dram read 2.1436 GB + write 2.1431 GB per launch at 25,600 meshes)",
+                             "traffic": traffic, "traffic_source": (f"{traffic_src}: ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the "
+                                                                    f"{(M + 7) // 8}-CTA lbs_tile_kernel launch") if traffic else None,
                              "ms": lbs_ms, "meshes": M, "bytes_per_mesh": LBS_BYTES_PER_MESH}}
+        line["roofline_encoder"] = {
+            "kernel": "ResNet-18 encoder (cast + stem2 + conv_patch + conv_tc + pools), " + args.encoder_mode, "bound": "tensor",
+            "achieved": ENC_FLOP * B / (enc_ms * 1e-3) / 1e12, "issued": issued * B / (enc_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+            "peak": pk.get("bf16_tflops"), "peak_kind": pk_kind + " (cuBLAS bf16 burst)",
+            "frac": ENC_FLOP * B / (enc_ms * 1e-3) / 1e12 / pk["bf16_tflops"], "frac_issued": issued * B / (enc_ms * 1e-3) / 1e12 / pk["bf16_tflops"],
+            "ms": enc_ms, "note": "achieved = algorithmic fp32 FLOPs of models/resnet.py (6.279 GFLOP/image); issued = tensor-core FLOPs actually "
+                                  "executed (split mode: three fp16 products per k-block, stem K padded 2646 -> 3136)"}
+        if ms_full is not None:
+            line["e2e_full"] = {"value": world * B / (ms_full * 1e-3), "unit": "images/s", "ms_per_step": ms_full,
+                                "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(d2h_bytes + 4 * B * N * 6890 * 3),
+                                "d2h": "everything `e2e` returns PLUS the (B,N,6890,3) sampled vertices north_star lists as an output (2.12 GB/step): "
+                                       "PCIe-bound in both directions; the reference's consumer (predict/...:157-165) keeps them on the device"}
+        if ms_stats is not None:
+            line["stats_gather"] = {"value": world * B / (ms_stats * 1e-3), "unit": "images/s", "ms_per_step": ms_stats,
+                                    "note": "same step, all-gather of (rotmats, betas, per-vertex uncertainty) only -- SURVEY.md 8f rank 1: the "
+                                            "consumer needs per-vertex statistics, not 8.3 MB of sample meshes per image"}
         if not args.no_cpu_baseline and world == 1:
             cb, _ = time_cpu_reference(2, 1, args.ref_batch, N)
             line["cpu_baseline"] = cb

@@ -14,7 +14,7 @@ from .pose_net import PoseMFShapeGaussianNet
 from .smpl import SMPL, SMPLOutput
 from .sampling import (pose_matrix_fisher_sampling_torch, compute_vertex_uncertainties_by_poseMF_shapeGaussian_sampling,
                        sample_meshes_batched, vertex_uncertainty, rank_samples_by_joints2d,
-                       joints2D_error_sorted_verts_sampling)
+                       joints2D_error_sorted_verts_sampling, check_sampler_status, SamplerShortfall)
 from .rigid import rot6d_to_rotmat
 from .pipeline import HotPathPipeline
 from .proxy import (CannyEdgeDetector, convert_2Djoints_to_gaussian_heatmaps_torch, proxy_representation,
@@ -24,4 +24,4 @@ __all__ = ["PoseMFShapeGaussianNet", "SMPL", "SMPLOutput", "pose_matrix_fisher_s
            "compute_vertex_uncertainties_by_poseMF_shapeGaussian_sampling", "sample_meshes_batched",
            "vertex_uncertainty", "rot6d_to_rotmat", "HotPathPipeline", "rank_samples_by_joints2d",
            "joints2D_error_sorted_verts_sampling", "CannyEdgeDetector", "convert_2Djoints_to_gaussian_heatmaps_torch",
-           "proxy_representation", "joints2d_heatmap_argmax"]
+           "proxy_representation", "joints2d_heatmap_argmax", "check_sampler_status", "SamplerShortfall"]

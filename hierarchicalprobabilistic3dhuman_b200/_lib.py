@@ -12,7 +12,7 @@ EXPORTS = [
     "hp3d_version", "hp3d_last_error",
     "hp3d_smpl_create", "hp3d_smpl_destroy", "hp3d_smpl_workspace_bytes", "hp3d_smpl_forward",
     "hp3d_smpl_shape_blend", "hp3d_smpl_pose_blend_workspace_bytes", "hp3d_smpl_pose_blend", "hp3d_smpl_lbs", "hp3d_rodrigues", "hp3d_rot6d_to_rotmat",
-    "hp3d_vertex_uncertainty", "hp3d_rank_samples_by_joints2d", "hp3d_mf_sample",
+    "hp3d_vertex_uncertainty", "hp3d_rank_samples_by_joints2d", "hp3d_mf_sample", "hp3d_mf_sample_sharded",
     "hp3d_head_create", "hp3d_head_destroy", "hp3d_head_workspace_bytes", "hp3d_head_forward",
     "hp3d_encoder_create", "hp3d_encoder_destroy", "hp3d_encoder_workspace_bytes", "hp3d_encoder_forward", "hp3d_encoder_forward_taps",
     "hp3d_encoder_forward_image", "hp3d_encoder_forward_argmax", "hp3d_crop_affine", "hp3d_heatmap_keypoints", "hp3d_mf_log_norm_constant", "hp3d_canny_edges", "hp3d_joints2d_to_heatmaps", "hp3d_proxy_rep", "hp3d_joints2d_heatmap_argmax",
@@ -75,6 +75,8 @@ def lib():
     L.hp3d_vertex_uncertainty.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.hp3d_mf_sample.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_uint64, c_uint64,
                                  c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    L.hp3d_mf_sample_sharded.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_uint64, c_uint64, c_uint64,
+                                         c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
     L.hp3d_head_create.argtypes = [POINTER(HeadWeights), POINTER(c_void_p)]
     L.hp3d_head_destroy.argtypes = [c_void_p]
     L.hp3d_head_workspace_bytes.argtypes = [c_void_p, c_int]
@@ -120,6 +122,25 @@ def require_cuda(t, name):
 def stream_ptr():
     import torch
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class nvtx:
+    """NVTX range around one stage of the path (`with _lib.nvtx("hp3d.encoder"):`), visible in nsys / ncu --nvtx timelines;
+    HP3D_NVTX=0 turns the ranges off (they cost ~0.1 us each without a profiler attached)."""
+    enabled = os.environ.get("HP3D_NVTX", "1") != "0"
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if nvtx.enabled:
+            import torch
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *a):
+        if nvtx.enabled:
+            import torch
+            torch.cuda.nvtx.range_pop()
 
 
 class Workspace:

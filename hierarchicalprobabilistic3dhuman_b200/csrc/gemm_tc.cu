@@ -571,18 +571,15 @@ int blend_tc_forward(void* p, const float* betas, int Mb, const float* body_pose
     a.n_chunk = std::max(1, std::min(18, cdiv(pairs * a.n_tiles, std::max(1, h->num_sms / 2))));
     a.n_chunks = cdiv(a.n_tiles, a.n_chunk);
     const int pgrid = 2 * std::max(1, std::min(pairs * a.n_chunks, h->num_sms / 2));
-    static bool setp = false;
-    if (!setp) { HP3D_CUDA(cudaFuncSetAttribute(blend_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem::TOTAL)); setp = true; }
+    HP3D_SMEM_OPT_IN(blend_pair_kernel, PairSmem::TOTAL);
     blend_pair_kernel<<<pgrid, 256, PairSmem::TOTAL, stream>>>(tmAhi, tmAlo, h->tmBhiHalf, h->tmBloHalf, tmOut, a);
     return launch_status("blend_pair_kernel");
   }
   if (h->passes == 3) {
-    static bool set = false;
-    if (!set) { HP3D_CUDA(cudaFuncSetAttribute(blend_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, BlendSmem<3>::TOTAL)); set = true; }
+    HP3D_SMEM_OPT_IN(blend_tc_kernel<3>, BlendSmem<3>::TOTAL);
     blend_tc_kernel<3><<<grid, 256, BlendSmem<3>::TOTAL, stream>>>(tmAhi, tmAlo, h->tmBhi, h->tmBlo, tmOut, a);
   } else {
-    static bool set = false;
-    if (!set) { HP3D_CUDA(cudaFuncSetAttribute(blend_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, BlendSmem<1>::TOTAL)); set = true; }
+    HP3D_SMEM_OPT_IN(blend_tc_kernel<1>, BlendSmem<1>::TOTAL);
     blend_tc_kernel<1><<<grid, 256, BlendSmem<1>::TOTAL, stream>>>(tmAhi, tmAlo, h->tmBhi, h->tmBlo, tmOut, a);
   }
   return launch_status("blend_tc_kernel");

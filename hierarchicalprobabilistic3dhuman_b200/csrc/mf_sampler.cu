@@ -47,7 +47,7 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, fl
 // the conversion step, so they live in shared memory and the rejection loop keeps ~20 live registers.
 __global__ void __launch_bounds__(768, 2) mf_sample_kernel(const float* __restrict__ U, const float* __restrict__ S,
                                                          const float* __restrict__ V, int B, int J, int N, float b,
-                                                         float m_star, uint64_t seed, uint64_t offset,
+                                                         float m_star, uint64_t seed, uint64_t offset, uint64_t image_offset,
                                                          const float* __restrict__ eps_in,
                                                          const float* __restrict__ w_in, int n_cand, int max_rounds,
                                                          float* __restrict__ R_out, unsigned long long* stats) {
@@ -104,7 +104,9 @@ __global__ void __launch_bounds__(768, 2) mf_sample_kernel(const float* __restri
         } else {
           valid = true;
           if (round >= max_rounds) break;
-          const uint64_t sub = ij * 32 + lane;
+          // Philox subsequence = GLOBAL (image, joint, lane): a rank that owns images [image_offset, image_offset + B) of a
+          // sharded batch draws exactly what a single GPU would draw for those images (results independent of world size)
+          const uint64_t sub = (ij + image_offset * (uint64_t)J) * 32 + lane;
           const uint64_t cnt = offset + 2ull * (uint64_t)round;
           const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
           const uint4 r0 = philox4x32_10(make_uint4((uint32_t)cnt, (uint32_t)(cnt >> 32), (uint32_t)sub, (uint32_t)(sub >> 32)), key);
@@ -191,6 +193,12 @@ __global__ void __launch_bounds__(768, 2) mf_sample_kernel(const float* __restri
 extern "C" int hp3d_mf_sample(const float* U, const float* S, const float* V, int B, int J, int N, float b,
                               uint64_t seed, uint64_t offset, const float* eps, const float* w, int oversampling,
                               float* R_out, unsigned long long* stats, void* stream) {
+  return hp3d_mf_sample_sharded(U, S, V, B, J, N, b, seed, offset, 0ull, eps, w, oversampling, R_out, stats, stream);
+}
+
+extern "C" int hp3d_mf_sample_sharded(const float* U, const float* S, const float* V, int B, int J, int N, float b,
+                                      uint64_t seed, uint64_t offset, uint64_t image_offset, const float* eps, const float* w,
+                                      int oversampling, float* R_out, unsigned long long* stats, void* stream) {
   HP3D_ARG(U && S && V && R_out, "null argument");
   HP3D_ARG(B > 0 && N > 0 && J > 0 && J <= 24, "need B>0, N>0, 0<J<=24");
   HP3D_ARG(b > 0.f && b < 4.f, "envelope parameter b must be in (0,4)");
@@ -198,15 +206,11 @@ extern "C" int hp3d_mf_sample(const float* U, const float* S, const float* V, in
   HP3D_ARG(!eps || oversampling > 0, "oversampling must be > 0 with injected noise");
   const float m_star = (float)(exp(-(4.0 - (double)b) / 2.0) * (4.0 / (double)b) * (4.0 / (double)b));
   const size_t smem = (size_t)CHUNK * J * 9 * sizeof(float) + (size_t)J * 64 * sizeof(float4) + (size_t)J * 20 * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    HP3D_CUDA(cudaFuncSetAttribute(mf_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
-  }
+  HP3D_SMEM_OPT_IN(mf_sample_kernel, 96 * 1024);
   const int n_cand = eps ? oversampling * N : 0;
   const int max_rounds = 64 + 16 * ((N + 31) / 32);     // Philox mode: acceptance >= 0.43 => ~2.3 rounds per 32
   const int grid = std::min(B, 148 * 2);
-  mf_sample_kernel<<<grid, J * 32, smem, (cudaStream_t)stream>>>(U, S, V, B, J, N, b, m_star, seed, offset, eps, w,
+  mf_sample_kernel<<<grid, J * 32, smem, (cudaStream_t)stream>>>(U, S, V, B, J, N, b, m_star, seed, offset, image_offset, eps, w,
                                                                  n_cand, max_rounds, R_out, stats);
   return launch_status("mf_sample_kernel");
 }

@@ -938,13 +938,10 @@ extern "C" int hp3d_smpl_shape_blend(const hp3d_smpl* h, const float* betas, int
   return launch_status("shape_blend_kernel");
 }
 
-static int g_blend_mode = -1;   // -1 unset; 0 fp32 CUDA-core; 1 tensor-core
-static int blend_mode() {
-  if (g_blend_mode < 0) {
-    const char* e = getenv("HP3D_BLEND");
-    g_blend_mode = (e && !strcmp(e, "fp32")) ? 0 : 1;
-  }
-  return g_blend_mode;
+// tuning / debugging knobs are read from the environment on every call (no process-global state; getenv is ~100 ns)
+static int blend_mode() {            // 0 fp32 CUDA-core; 1 tensor-core
+  const char* e = getenv("HP3D_BLEND");
+  return (e && !strcmp(e, "fp32")) ? 0 : 1;
 }
 
 extern "C" int hp3d_smpl_pose_blend(const hp3d_smpl* h, const float* betas, const float* v_shaped, int Mb,
@@ -965,13 +962,13 @@ extern "C" int hp3d_smpl_lbs(const hp3d_smpl* h, const float* v_posed, const flo
                              float* joints, void* stream) {
   HP3D_ARG(h && v_posed && J && global_orient && body_pose && vertices, "null argument");
   HP3D_ARG(M > 0 && Mb > 0 && Mg > 0 && M % Mb == 0 && M % Mg == 0, "M must be a multiple of Mb and Mg");
-  static int force_generic = -1;
-  if (force_generic < 0) { const char* e = getenv("HP3D_LBS"); force_generic = (e && !strcmp(e, "generic")) ? 1 : 0; }
+  int force_generic = 0;
+  { const char* e = getenv("HP3D_LBS"); force_generic = (e && !strcmp(e, "generic")) ? 1 : 0; }
   if (h->tile_nq_max > 0 && !force_generic) {
     // HP3D_LBS_MODE (tuning sweeps): 0 = scalar FFMA, 2 meshes ahead; 1 = FFMA2, 2 ahead; 2 = FFMA2, 4 ahead;
     // 3 = scalar FFMA, 4 ahead. Default: LBS_DEFAULT_MODE.
-    static int mode = -1;
-    if (mode < 0) { const char* e = getenv("HP3D_LBS_MODE"); mode = (e && *e >= '0' && *e <= '3') ? (*e - '0') : LBS_DEFAULT_MODE; }
+    int mode = LBS_DEFAULT_MODE;
+    { const char* e = getenv("HP3D_LBS_MODE"); if (e && *e >= '0' && *e <= '3') mode = *e - '0'; }
     const int grid = cdiv(M, LBS_GMAX);
 #define HP3D_LBS_LAUNCH(NQM, F2, PF)                                                                                   \
     lbs_tile_kernel<NQM, F2, PF, LBS_GMAX><<<grid, 256, 0, (cudaStream_t)stream>>>(v_posed, J, Mb, global_orient, Mg, body_pose, M, \
@@ -1034,25 +1031,23 @@ extern "C" int hp3d_rot6d_to_rotmat(const float* x, int n, float* R, void* strea
 extern "C" int hp3d_vertex_uncertainty(const float* vertices, int B, int N, float* mean_vertices, float* avg_dist,
                                        void* stream) {
   HP3D_ARG(vertices && avg_dist && B > 0 && N > 0, "bad argument");
-  static int variant = -1;       // HP3D_UNC: 1 = 32-vertex tiles, 4-byte loads; 2 = 64-vertex tiles, 8-byte loads; 3 = 64-vertex tiles, cp.async
-  if (variant < 0) { const char* e = getenv("HP3D_UNC"); variant = (e && *e >= '1' && *e <= '3') ? (*e - '0') : UNC_DEFAULT_VARIANT; }
+  int variant = UNC_DEFAULT_VARIANT;   // HP3D_UNC: 1 = 32-vertex tiles, 4-byte loads; 2 = 64-vertex tiles, 8-byte loads; 3 = 64-vertex tiles, cp.async
+  { const char* e = getenv("HP3D_UNC"); if (e && *e >= '1' && *e <= '3') variant = *e - '0'; }
   const size_t smem2 = ((size_t)N * UNC2_F + UNC2_F + 256) * sizeof(float);
   if (variant >= 2 && smem2 <= 110 * 1024) {
-    static size_t attr2[2] = {0, 0};
     dim3 grid(cdiv(NV, UNC2_TV), B);
     if (variant == 2) {
-      if (smem2 > attr2[0]) { HP3D_CUDA(cudaFuncSetAttribute(vertex_uncertainty_smem2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); attr2[0] = smem2; }
+      HP3D_SMEM_OPT_IN(vertex_uncertainty_smem2_kernel<false>, 110 * 1024);      // per device, to the largest size this path uses
       vertex_uncertainty_smem2_kernel<false><<<grid, 256, smem2, (cudaStream_t)stream>>>(vertices, B, N, mean_vertices, avg_dist);
     } else {
-      if (smem2 > attr2[1]) { HP3D_CUDA(cudaFuncSetAttribute(vertex_uncertainty_smem2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); attr2[1] = smem2; }
+      HP3D_SMEM_OPT_IN(vertex_uncertainty_smem2_kernel<true>, 110 * 1024);
       vertex_uncertainty_smem2_kernel<true><<<grid, 256, smem2, (cudaStream_t)stream>>>(vertices, B, N, mean_vertices, avg_dist);
     }
     return launch_status("vertex_uncertainty_smem2_kernel");
   }
   const size_t smem = ((size_t)N * UNC_F + UNC_F + 256) * sizeof(float);
   if (smem <= 220 * 1024) {
-    static size_t attr = 0;
-    if (smem > attr) { HP3D_CUDA(cudaFuncSetAttribute(vertex_uncertainty_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    HP3D_SMEM_OPT_IN(vertex_uncertainty_smem_kernel, 220 * 1024);
     dim3 grid(cdiv(NV, UNC_TV), B);
     vertex_uncertainty_smem_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(vertices, B, N, mean_vertices, avg_dist);
     return launch_status("vertex_uncertainty_smem_kernel");

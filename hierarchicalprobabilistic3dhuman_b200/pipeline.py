@@ -18,10 +18,12 @@ from .sampling import pose_matrix_fisher_sampling_torch
 
 class HotPathPipeline:
     def __init__(self, net, smpl, batch, num_samples, device, rotmats_out=None, betas_out=None, vertices_out=None,
-                 uncertainty_out=None, chunks=4, on_vertices_chunk=None):
+                 uncertainty_out=None, chunks=4, on_vertices_chunk=None, image_offset=0):
         """`vertices_out` may be one (B,N,6890,3) tensor or a list of equally sized chunk tensors (cb,N,6890,3) --
         e.g. this rank's slices of per-chunk all-gather buffers; `on_vertices_chunk(c)` is then called right after
-        chunk c's SMPL kernels are enqueued, so a collective on another stream can overlap the next chunk."""
+        chunk c's SMPL kernels are enqueued, so a collective on another stream can overlap the next chunk.
+        `image_offset`: global index of this pipeline's first image when the batch is sharded over ranks (keys the sampler's
+        Philox stream, so results do not depend on the world size)."""
         self.net, self.smpl, self.B, self.N, self.dev = net, smpl, batch, num_samples, torch.device(device)
         B, N, dev = batch, num_samples, self.dev
         mk = lambda t, *s: t if t is not None else torch.empty(*s, device=dev, dtype=torch.float32)
@@ -35,6 +37,7 @@ class HotPathPipeline:
             self.vertices = mk(vertices_out, B, N, 6890, 3)
             self.vertex_chunks = [self.vertices]
         self.on_vertices_chunk = on_vertices_chunk
+        self.image_offset = int(image_offset)
         self.uncertainty = mk(uncertainty_out, B, 6890)
         for t in [self.rotmats, self.betas, self.uncertainty] + self.vertex_chunks:
             assert t.is_contiguous() and t.device == dev
@@ -55,21 +58,26 @@ class HotPathPipeline:
     # ------------------------------------------------------------------ device-resident pass
     def _after_encoder(self, feats, proxy_rep=None, joints2d=None, joints2d_px=None):
         L, B, N = self.L, self.B, self.N
-        F, U, S, V, mode, shape_params, glob, cam = self.net.head(feats)
-        loc = shape_params[:, :10].contiguous()
-        glob_R = rot6d_to_rotmat(glob)
-        out_mode = self.smpl(body_pose=mode, global_orient=glob_R.unsqueeze(1), betas=loc, pose2rot=False)
-        R = pose_matrix_fisher_sampling_torch(U, S, V, N, out=self.rotmats)
+        with _lib.nvtx("hp3d.head"):
+            F, U, S, V, mode, shape_params, glob, cam = self.net.head(feats)
+            loc = shape_params[:, :10].contiguous()
+            glob_R = rot6d_to_rotmat(glob)
+        with _lib.nvtx("hp3d.smpl_mode"):
+            out_mode = self.smpl(body_pose=mode, global_orient=glob_R.unsqueeze(1), betas=loc, pose2rot=False)
+        with _lib.nvtx("hp3d.mf_sampler"):
+            R = pose_matrix_fisher_sampling_torch(U, S, V, N, out=self.rotmats, image_offset=self.image_offset)
         self.betas.copy_(loc)
         C = len(self.vertex_chunks)
         cb = B // C
         for c, vch in enumerate(self.vertex_chunks):       # images [c*cb, (c+1)*cb): SMPL on cb*N meshes + statistics
             i0 = c * cb
-            _lib.check(L.hp3d_smpl_forward(self.h_smpl, loc[i0:].data_ptr(), cb, glob_R[i0:].data_ptr(), cb, R[i0:].data_ptr(),
-                                           cb * N, vch.data_ptr(), self.joints[i0 * N:].data_ptr(), self.ws.data_ptr(),
-                                           self.ws.numel(), _lib.stream_ptr()), "hp3d_smpl_forward")
-            _lib.check(L.hp3d_vertex_uncertainty(vch.data_ptr(), cb, N, None, self.uncertainty[i0:].data_ptr(),
-                                                 _lib.stream_ptr()), "hp3d_vertex_uncertainty")
+            with _lib.nvtx("hp3d.smpl_samples"):
+                _lib.check(L.hp3d_smpl_forward(self.h_smpl, loc[i0:].data_ptr(), cb, glob_R[i0:].data_ptr(), cb, R[i0:].data_ptr(),
+                                               cb * N, vch.data_ptr(), self.joints[i0 * N:].data_ptr(), self.ws.data_ptr(),
+                                               self.ws.numel(), _lib.stream_ptr()), "hp3d_smpl_forward")
+            with _lib.nvtx("hp3d.vertex_uncertainty"):
+                _lib.check(L.hp3d_vertex_uncertainty(vch.data_ptr(), cb, N, None, self.uncertainty[i0:].data_ptr(),
+                                                     _lib.stream_ptr()), "hp3d_vertex_uncertainty")
             if self.on_vertices_chunk is not None:
                 self.on_vertices_chunk(c)
         res = dict(mode_vertices=out_mode.vertices, mode_joints=out_mode.joints, joints=self.joints, rotmats=R,
@@ -77,7 +85,8 @@ class HotPathPipeline:
         if proxy_rep is not None or joints2d is not None or joints2d_px is not None:
             # rank the N samples of every image by 2D-joint consistency (sampling_utils.py:195-233)
             from .sampling import rank_samples_by_joints2d
-            rk = rank_samples_by_joints2d(self.joints.view(B, N, 90, 3), proxy_rep, cam, joints2d=joints2d, joints2d_px=joints2d_px,
+            with _lib.nvtx("hp3d.rank_samples"):
+              rk = rank_samples_by_joints2d(self.joints.view(B, N, 90, 3), proxy_rep, cam, joints2d=joints2d, joints2d_px=joints2d_px,
                                           img_wh=proxy_rep.shape[-1] if proxy_rep is not None else 256)
             res["sample_order"], res["sample_error"] = rk["order"], rk["error"]
         return res
@@ -85,14 +94,16 @@ class HotPathPipeline:
     def run_device(self, x_dev):
         """x_dev (B,18,256,256) fp32 on the GPU -> dict of device tensors (sample vertices live in `vertices`)."""
         with torch.cuda.device(self.dev):
-            feats, j2d, vis = self.net.encode(x_dev, return_joints2d=True)     # heat-map arg-max rides on the input pass
+            with _lib.nvtx("hp3d.encoder"):
+                feats, j2d, vis = self.net.encode(x_dev, return_joints2d=True)     # heat-map arg-max rides on the input pass
             return self._after_encoder(feats, joints2d_px=(j2d, vis))
 
     def run_device_images(self, rgb, joints2D, visibility=None):
         """Image-space input: (B,3,256,256) RGB crops in [0,1], (B,17,2) joints, (B,17)
         visibility on the GPU -> the same dict as `run_device`; proxy representation generated in-kernel."""
         with torch.cuda.device(self.dev):
-            feats = self.net.encode_image(rgb, joints2D, visibility)
+            with _lib.nvtx("hp3d.encoder_from_image"):
+                feats = self.net.encode_image(rgb, joints2D, visibility)
             return self._after_encoder(feats, None, joints2d=(joints2D, visibility))
 
     # ------------------------------------------------------------------ host-streaming pass
@@ -111,12 +122,27 @@ class HotPathPipeline:
                 h2d=torch.cuda.Stream(device=dev), d2h=torch.cuda.Stream(device=dev))
         return self._stage
 
-    def run_host(self, x_host):
+    def release_host_vertices(self):
+        """free the 2 x (B,N,6890,3) pinned host buffers `run_host(..., return_vertices=True)` allocated"""
+        if self._stage is not None:
+            for o in self._stage["out"]:
+                o.pop("vertices", None)
+
+    def run_host(self, x_host, return_vertices=False):
         """x_host: pinned (B,18,256,256) fp32 HOST tensor. Returns (dict of pinned host result tensors, event);
         the results are valid once `event.synchronize()` returns. Calls may be issued back to back: copies of
-        call i+1 overlap the kernels of call i."""
+        call i+1 overlap the kernels of call i. `return_vertices=True` also copies the (B,N,6890,3) sampled vertices back
+        (8.3 MB per image: the reference's consumer keeps them on the device, predict/...:157-165)."""
         assert x_host.is_pinned() and x_host.shape[0] == self.B
         st = self._staging(x_host)
+        if return_vertices:
+            assert self.vertices is not None, "return_vertices needs a single (B,N,6890,3) vertices buffer"
+            for o in st["out"]:
+                if "vertices" not in o:
+                    o["vertices"] = torch.empty(self.B, self.N, 6890, 3, dtype=torch.float32).pin_memory()
+        else:
+            for o in st["out"]:
+                o.pop("vertices", None)
         slot = self._slot
         self._slot ^= 1
         B, C = self.B, self.chunks

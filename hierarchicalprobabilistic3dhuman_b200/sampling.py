@@ -8,7 +8,56 @@ import torch
 
 from . import _lib
 
-_stats_buf = {}
+
+
+class SamplerShortfall(RuntimeError):
+    """The rejection loop of some (image, joint) pair ran out of proposals (see `check_sampler_status`)."""
+
+
+class _StatusRing:
+    """Asynchronous shortfall watch. The reference redraws ALL proposals of an (image, joint) pair when fewer than N were
+    accepted (utils/sampling_utils.py:50,68-69); the kernel instead draws until N are accepted and gives up only after a
+    bound that is never reached in practice (acceptance >= 0.43, 8x / Philox: (64 + N/2) x 32 proposals) -- in which case it
+    fills the remaining samples with the mode and counts the pair in stats[2]. That must not pass silently: every call
+    copies its counter to pinned host memory behind the kernel (no sync), and the NEXT call on the device (or an explicit
+    `check_sampler_status()`) raises if a previous launch reported a shortfall."""
+
+    def __init__(self):
+        self.pending = {}      # device index -> list of (event, pinned tensor)
+
+    def post(self, dev, stats):
+        host = torch.empty(3, dtype=torch.int64).pin_memory()
+        host.copy_(stats, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        self.pending.setdefault(dev.index, []).append((ev, host))
+
+    def poll(self, dev=None, wait=False):
+        for idx in ([dev.index] if dev is not None else list(self.pending)):
+            keep = []
+            for ev, host in self.pending.get(idx, []):
+                if wait:
+                    ev.synchronize()
+                if ev.query():
+                    if int(host[2]) > 0:
+                        self.pending[idx] = []
+                        raise SamplerShortfall(
+                            f"matrix-Fisher sampler: {int(host[2])} (image, joint) chunk(s) ran out of proposals and were "
+                            f"completed with the distribution mode ({int(host[1])} accepted of {int(host[0])} proposals). "
+                            "With injected noise pass more candidates (oversampling_ratio); the reference would redraw "
+                            "(utils/sampling_utils.py:68-69).")
+                else:
+                    keep.append((ev, host))
+            self.pending[idx] = keep
+
+
+_status = _StatusRing()
+
+
+def check_sampler_status(device=None):
+    """Block until every sampler launch issued so far (on `device`, default all) has reported, and raise SamplerShortfall
+    if one of them ran out of proposals."""
+    _status.poll(torch.device(device) if device is not None else None, wait=True)
 
 
 def _rng_seed_offset(device, n_rounds_bound):
@@ -22,13 +71,17 @@ def _rng_seed_offset(device, n_rounds_bound):
 
 
 def pose_matrix_fisher_sampling_torch(pose_U, pose_S, pose_V, num_samples, b=1.5, oversampling_ratio=8,
-                                      sample_on_cpu=False, noise=None, return_stats=False, out=None):
+                                      sample_on_cpu=False, noise=None, return_stats=False, out=None, image_offset=0):
     """(B,J,3,3),(B,J,3),(B,J,3,3) -> (B,num_samples,J,3,3) rotation samples of M(U S V^T).
     `sample_on_cpu` is accepted for signature compatibility and ignored (everything runs in one
     kernel). `noise=(eps, w)` with eps (B,J,oversampling_ratio*N,4) standard normals and
     w (B,J,oversampling_ratio*N) uniforms replays the reference's accept/compact rule exactly;
     without it an in-kernel Philox stream seeded from torch's CUDA generator is used.
-    `out` may be a slice of a larger (e.g. all-gather) buffer."""
+    `out` may be a slice of a larger (e.g. all-gather) buffer. `image_offset`: index of pose_U[0] in the GLOBAL batch when
+    the batch is sharded over ranks -- the Philox stream is keyed by the global image index, so with the same generator
+    state on every rank the gathered samples do not depend on the world size.
+    A shortfall of the rejection loop (reference: redraw, :68-69) raises SamplerShortfall -- immediately with injected
+    noise, at the next call / `check_sampler_status()` in the asynchronous Philox mode."""
     _lib.require_cuda(pose_U, "pose_U")
     dev = pose_U.device
     B, J = pose_U.shape[0], pose_U.shape[1]
@@ -48,11 +101,18 @@ def pose_matrix_fisher_sampling_torch(pose_U, pose_S, pose_V, num_samples, b=1.5
     else:
         seed, off = _rng_seed_offset(dev, 64 + 16 * ((num_samples + 31) // 32))
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().hp3d_mf_sample(U.data_ptr(), S.data_ptr(), V.data_ptr(), B, J, num_samples, float(b),
-                                             seed, off, eps_p, w_p, int(oversampling_ratio), out.data_ptr(),
-                                             stats.data_ptr(), _lib.stream_ptr()), "hp3d_mf_sample")
-    if return_stats:
-        return out, stats
+        _status.poll(dev)                      # a shortfall reported by an EARLIER launch surfaces here (no sync)
+        _lib.check(_lib.lib().hp3d_mf_sample_sharded(U.data_ptr(), S.data_ptr(), V.data_ptr(), B, J, num_samples, float(b),
+                                                     seed, off, int(image_offset), eps_p, w_p, int(oversampling_ratio),
+                                                     out.data_ptr(), stats.data_ptr(), _lib.stream_ptr()), "hp3d_mf_sample_sharded")
+        if return_stats:
+            return out, stats
+        if noise is not None:                  # parity / replay mode: not a hot path, check right away
+            if int(stats[2].item()) > 0:
+                raise SamplerShortfall(f"injected noise exhausted for {int(stats[2].item())} (image, joint) chunk(s): the reference "
+                                       "would redraw a fresh block (utils/sampling_utils.py:68-69); pass more candidates")
+        else:
+            _status.post(dev, stats)
     return out
 
 

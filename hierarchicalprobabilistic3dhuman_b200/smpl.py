@@ -87,7 +87,8 @@ class SMPL(nn.Module):
 
     # ------------------------------------------------------------------ handle management
     def _handle(self, device):
-        key = torch.device(device).index or 0
+        idx = torch.device(device).index
+        key = idx if idx is not None else torch.cuda.current_device()    # an index-less 'cuda' device is the CURRENT one
         h = self._handles.get(key)
         if h is None:
             L = _lib.lib()
@@ -149,6 +150,9 @@ class SMPL(nn.Module):
                 full_pose = torch.cat([go, bp], dim=1)
                 body_pose_out, global_orient_out = bp, go
             else:
+                if body_pose is None or global_orient is None:
+                    raise ValueError("SMPL.forward(pose2rot=False) needs body_pose (M,23,3,3) and global_orient (M,1,3,3) rotation "
+                                     "matrices (the stored default parameters are axis-angle)")
                 bp_r = f32(body_pose).reshape(-1, 23, 3, 3)
                 go_r = f32(global_orient).reshape(-1, 1, 3, 3)
                 M = bp_r.shape[0]
@@ -166,8 +170,13 @@ class SMPL(nn.Module):
                                            verts.data_ptr(), joints.data_ptr(), ws.data_ptr(), ws.numel(),
                                            _lib.stream_ptr()), "hp3d_smpl_forward")
             if transl is not None:
-                verts = verts + transl.to(dev)[:, None]
-                joints = joints + transl.to(dev)[:, None]
+                # smplx translates vertices and its 45 joints AFTER lbs(); the reference's three extra regressors
+                # (models/smpl_official.py:30-32) then act on the TRANSLATED vertices, i.e. joint r moves by rowsum_r * transl
+                t = f32(transl).reshape(-1, 1, 3)
+                verts = verts + t
+                rs = torch.ones(90, device=dev, dtype=torch.float32)
+                rs[45:] = torch.as_tensor(self._model["joint_regressors_extra"].sum(axis=1), dtype=torch.float32, device=dev)
+                joints = joints + rs[None, :, None] * t
             if full_pose is None:
                 go_full = go_r if Mg == M else go_r.repeat_interleave(M // Mg, dim=0)
                 full_pose = torch.cat([go_full, bp_r], dim=1)

@@ -10,7 +10,11 @@
  *  - all tensor memory is caller-owned DEVICE memory (fp32, contiguous, 16-byte aligned base
  *    pointers unless noted); model constants passed to *_create are HOST pointers and are copied /
  *    repacked into an immutable opaque handle.
- *  - kernels are enqueued on the given stream; no internal synchronisation, no global state.
+ *  - kernels are enqueued on the given stream; no internal synchronisation. The library keeps no mutable state that changes
+ *    results: its only process-level data are idempotent per-DEVICE caches (which kernels have been opted in to > 48 KB of
+ *    shared memory on which device ordinal; the driver entry point of cuTensorMapEncodeTiled) and a thread-local error
+ *    string, so one process may drive several GPUs and several host threads. Tuning knobs (HP3D_* environment variables,
+ *    documented where they are read) are looked up per call, never cached.
  *  - `stream` is a cudaStream_t passed as void* so the header needs no CUDA include.
  */
 #ifndef HP3D_H_
@@ -133,6 +137,13 @@ int hp3d_heatmap_keypoints(const float* heatmaps, int B, int K, int h, int w, fl
 int hp3d_mf_sample(const float* U, const float* S, const float* V, int B, int J, int N, float b,
                    uint64_t seed, uint64_t offset, const float* eps, const float* w, int oversampling,
                    float* R_out, unsigned long long* stats, void* stream);
+/* The same for one SHARD of a batch (the reference has no multi-GPU path): the B images passed are images
+ * [image_offset, image_offset + B) of the global batch. The in-kernel Philox stream is keyed by the GLOBAL (image, joint,
+ * lane), so with the same (seed, offset) on every rank the gathered samples are bit-identical to a single-GPU run on the
+ * concatenated batch, whatever the world size. hp3d_mf_sample == image_offset 0. */
+int hp3d_mf_sample_sharded(const float* U, const float* S, const float* V, int B, int J, int N, float b,
+                           uint64_t seed, uint64_t offset, uint64_t image_offset, const float* eps, const float* w,
+                           int oversampling, float* R_out, unsigned long long* stats, void* stream);
 
 /* matrix-Fisher normalising constant, replaces losses/matrix_fisher_loss.py:134-192
  * (LogMFNormConstant.forward / backward): S_proper [n*3] proper singular values (s1 >= s2 >= |s3|) -> log_c [n] =
