@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"],
                     help="N>1 vertices gather: copy-engine peer pushes over symmetric memory (p2p), NCCL all-gather, or "
                          "auto = p2p when the symmetric-memory rendezvous works, else NCCL")
+    ap.add_argument("--push", default=None, choices=["mc", "kernel", "ce"],
+                    help="p2p transport: hp3d_peer_push (SM stores over NVLink from small co-resident CTAs; default) or copy engines")
+    ap.add_argument("--push-ctas", type=int, default=None, help="CTAs of the peer-push kernel (default 296)")
     ap.add_argument("--sm-limit", type=int, default=-1,
                     help="CTAs of the persistent tensor-core kernels (experiment: leave SMs to a co-running NCCL gather; "
                          "-1 / 0 = all SMs, the default -- 116 of 148 brought nothing at 4 GPUs)")
@@ -237,6 +240,10 @@ def main_hp3d(args):
         if os.environ.get("HP3D_NCCL_PRIO", "1") == "1":
             opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
         dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+    # everything issued on the COMM stream (vertices gather, push fences) gets its own communicator: ProcessGroupNCCL runs all
+    # collectives of one group on a single internal stream, so sharing the default group would make the small per-step gathers
+    # of the main stream queue behind the previous step's vertices transfer (= no overlap at all, the round-1 behaviour)
+    pg_comm = dist.new_group(backend="nccl") if world > 1 else None
     B, N = args.batch, args.samples
     import __graft_entry__
     if rank == 0:
@@ -266,15 +273,18 @@ def main_hp3d(args):
     NBUF = 2 if (full and world > 1) else 1
     from hierarchicalprobabilistic3dhuman_b200.distributed import SymmPush
     pushers = None
-    # transport policy (measured, profiles/README.md): 2 GPUs -> copy-engine pushes (6.5 vs 8.8 ms/step); >= 4 GPUs -> NCCL
-    # (14.7 vs 16.0 ms/step at 4 GPUs: the step is bound by the 6.4 GB each rank receives, NCCL moves it faster)
+    # transport policy (measured at 4 GPUs, profiles/r02k_4gpu_sweep.txt, ms per step; no-communication floor 8.7):
+    #   NCCL all-gather on its OWN communicator 14.3 | copy-engine pushes 15.8 | unicast peer-store kernel 16.1 |
+    #   NVLS multicast-store kernel 17.5-18.9  (all pushes move ~400 GB/s per rank and direction; NCCL's NVLS gather ~730 GB/s
+    #   but its CTAs only partly co-run with the hot path's kernels).  2 GPUs: copy-engine pushes (9.4 vs 9.1 floor).
     want_p2p = args.transport == "p2p" or (args.transport == "auto" and world == 2)
     if world > 1 and full and not want_p2p:
         lim = args.sm_limit
         if lim > 0:
             os.environ["HP3D_SM_LIMIT"] = str(lim)
     if world > 1 and full and want_p2p:
-        pushers = [SymmPush((VC, world, cbv, N, 6890, 3), dev, rank, world) for _ in range(NBUF)]
+        pushers = [SymmPush((VC, world, cbv, N, 6890, 3), dev, rank, world, mode=args.push or "ce", ctas=args.push_ctas, fence_group=pg_comm)
+                   for _ in range(NBUF)]
         g_verts = [p_.full for p_ in pushers]
         if not all(p_.ok for p_ in pushers):
             if rank == 0:
@@ -286,7 +296,10 @@ def main_hp3d(args):
     comm_stream = torch.cuda.Stream(device=dev)
     state = {"k": 0, "pending": [None] * NBUF, "count": 0, "verts": True}
 
-    transport = "p2p-copy-engine (symmetric memory)" if pushers else ("nccl" if (world > 1 and full) else "none")
+    transport = ({"mc": "NVLS multicast-store kernel (hp3d_peer_push_multicast, symmetric memory)",
+                  "kernel": "p2p peer-store kernel (hp3d_peer_push, symmetric memory)",
+                  "ce": "p2p-copy-engine (symmetric memory)"}[pushers[0].mode]
+                 if pushers else ("nccl" if (world > 1 and full) else "none"))
 
     def on_chunk(c):
         if world > 1 and full and state["verts"]:
@@ -298,7 +311,7 @@ def main_hp3d(args):
                 pushers[state["k"]].push(lambda buf, c=c: buf[c, my], comm_stream)
             else:
                 with torch.cuda.stream(comm_stream):
-                    dist.all_gather_into_tensor(gv[c].view(world * cbv, N, 6890, 3), gv[c, my])
+                    dist.all_gather_into_tensor(gv[c].view(world * cbv, N, 6890, 3), gv[c, my], group=pg_comm)
 
     pipe = hp.HotPathPipeline(net, smpl, B, N, dev, rotmats_out=gb.local("rotmats"), betas_out=gb.local("betas"),
                               vertices_out=[g_verts[0][c, my] for c in range(VC)], uncertainty_out=gb.local("uncertainty"),

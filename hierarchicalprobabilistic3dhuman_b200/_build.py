@@ -7,7 +7,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libhp3d.so")
 HOST_SHIM_PATH = os.path.join(PKG_DIR, "libhp3d_hostshim.so")
-SOURCES = ["api.cu", "smpl.cu", "mf_sampler.cu", "mf_head.cu", "encoder.cu", "conv_tc.cu", "gemm_tc.cu", "rank.cu", "proxy.cu", "crop.cu", "mf_norm.cu"]
+SOURCES = ["api.cu", "smpl.cu", "smpl_fused.cu", "mf_sampler.cu", "mf_head.cu", "encoder.cu", "conv_tc.cu", "gemm_tc.cu", "rank.cu", "proxy.cu", "crop.cu", "mf_norm.cu", "peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

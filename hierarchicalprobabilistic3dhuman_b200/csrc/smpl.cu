@@ -39,6 +39,7 @@ struct hp3d_smpl {
   int* pick_ids = nullptr;       // [NPICK]
   SmplTree tree;
   void* blend_tc = nullptr;      // tensor-core pose-blend operands (gemm_tc.cu), optional
+  void* fused = nullptr;         // fused blend + skinning + statistics plan (smpl_fused.cu), optional
   // tile-local skinning tables (64-vertex tiles): distinct joints of the tile + dense per-vertex weights
   int tile_nq_max = 0;           // 0 => tables unavailable (some tile touches > 12 joints): generic kernel
   int* tile_nq = nullptr;        // [NT]
@@ -767,6 +768,13 @@ namespace hp3d {
 int blend_tc_create(const double* posedirs, const double* shapedirs, const double* v_template, void** out);   // gemm_tc.cu
 void blend_tc_destroy(void* p);
 size_t blend_tc_workspace_bytes(int M);
+int smpl_fused_create(const hp3d_smpl_model* md, const float* Jt, const float* Js, void** out);       // smpl_fused.cu
+void smpl_fused_destroy(void* p);
+size_t smpl_fused_workspace_bytes(int M);
+void smpl_fused_info(const void* p, int* permuted, int* nq_sum, int* nq_max);
+int smpl_fused_forward(void* p, const float* betas, int Mb, const float* global_orient, int Mg, const float* body_pose, int M,
+                       int samples_per_image, float* vertices, float* joints, float* unc, float* mean, void* workspace,
+                       cudaStream_t stream);
 int blend_tc_forward(void* p, const float* betas, int Mb, const float* body_pose, int M, float* v_posed,
                      void* workspace, cudaStream_t stream);
 }
@@ -902,6 +910,7 @@ extern "C" int hp3d_smpl_create(const hp3d_smpl_model* md, hp3d_smpl** out) {
   rc = rc ? rc : upload(&h->tile_joff, tjoff.data(), tjoff.size());
   rc = rc ? rc : upload(&h->tile_w, tw.data(), tw.size());
   rc = rc ? rc : blend_tc_create(md->posedirs, md->shapedirs, md->v_template, &h->blend_tc);
+  rc = rc ? rc : smpl_fused_create(md, Jt.data(), Js.data(), &h->fused);
   if (rc) { hp3d_smpl_destroy(h); return rc; }
   *out = h;
   return 0;
@@ -915,6 +924,7 @@ extern "C" void hp3d_smpl_destroy(hp3d_smpl* h) {
   cudaFree(h->tile_nq); cudaFree(h->tile_joff); cudaFree(h->tile_w);
   cudaFree(h->tile_ustart); cudaFree(h->tile_uent); cudaFree(h->reg_slot); cudaFree(h->pick_slot);
   blend_tc_destroy(h->blend_tc);
+  smpl_fused_destroy(h->fused);
   delete h;
 }
 
@@ -924,9 +934,24 @@ static size_t ws_vposed(int M) { return align_up((size_t)M * VPITCH * sizeof(flo
 
 extern "C" size_t hp3d_smpl_pose_blend_workspace_bytes(int M) { return M > 0 ? blend_tc_workspace_bytes(M) : 0; }
 
-extern "C" size_t hp3d_smpl_workspace_bytes(const hp3d_smpl*, int M, int Mb) {
+// HP3D_SMPL=staged selects the round-1 three-kernel path (blend GEMM -> v_posed in HBM -> LBS); default: the fused kernel
+static bool use_fused(const hp3d_smpl* h) {
+  if (!h->fused) return false;
+  const char* e = getenv("HP3D_SMPL");
+  return e && !strcmp(e, "fused");          // TODO(default): flip once verified on hardware
+}
+
+extern "C" size_t hp3d_smpl_workspace_bytes(const hp3d_smpl* h, int M, int Mb) {
   if (M <= 0 || Mb <= 0) return 0;
+  if (h && use_fused(h)) return smpl_fused_workspace_bytes(M);
   return ws_vshaped(Mb) + ws_J(Mb) + ws_vposed(M) + blend_tc_workspace_bytes(M);
+}
+
+extern "C" int hp3d_smpl_layout_info(const hp3d_smpl* h, int* fused, int* permuted, int* tile_joint_sum, int* tile_joint_max) {
+  HP3D_ARG(h, "null handle");
+  if (fused) *fused = use_fused(h) ? 1 : 0;
+  smpl_fused_info(h->fused, permuted, tile_joint_sum, tile_joint_max);
+  return 0;
 }
 
 extern "C" int hp3d_smpl_shape_blend(const hp3d_smpl* h, const float* betas, int Mb, float* v_shaped, float* J,
@@ -1005,6 +1030,9 @@ extern "C" int hp3d_smpl_forward(const hp3d_smpl* h, const float* betas, int Mb,
   HP3D_ARG(h && betas && global_orient && body_pose && vertices && workspace, "null argument");
   HP3D_ARG(M > 0 && Mb > 0 && Mg > 0 && M % Mb == 0 && M % Mg == 0, "M must be a multiple of Mb and Mg");
   HP3D_ARG(workspace_bytes >= hp3d_smpl_workspace_bytes(h, M, Mb), "workspace too small");
+  if (use_fused(h))
+    return smpl_fused_forward(h->fused, betas, Mb, global_orient, Mg, body_pose, M, 0, vertices, joints, nullptr, nullptr, workspace,
+                              (cudaStream_t)stream);
   char* ws = (char*)workspace;
   float* v_shaped = (float*)ws; ws += ws_vshaped(Mb);
   float* J = (float*)ws; ws += ws_J(Mb);
@@ -1014,6 +1042,21 @@ extern "C" int hp3d_smpl_forward(const hp3d_smpl* h, const float* betas, int Mb,
   rc = hp3d_smpl_pose_blend(h, betas, v_shaped, Mb, body_pose, M, v_posed, ws, blend_tc_workspace_bytes(M), stream);
   if (rc) return rc;
   return hp3d_smpl_lbs(h, v_posed, J, Mb, global_orient, Mg, body_pose, M, vertices, joints, stream);
+}
+
+extern "C" int hp3d_smpl_forward_stats(const hp3d_smpl* h, const float* betas, int Mb, const float* global_orient, int Mg,
+                                       const float* body_pose, int M, int samples_per_image, float* vertices, float* joints,
+                                       float* avg_dist, float* mean_vertices, void* workspace, size_t workspace_bytes, void* stream) {
+  HP3D_ARG(h && betas && global_orient && body_pose && vertices && workspace && avg_dist, "null argument");
+  HP3D_ARG(M > 0 && Mb > 0 && Mg > 0 && M % Mb == 0 && M % Mg == 0, "M must be a multiple of Mb and Mg");
+  HP3D_ARG(samples_per_image > 0 && M % samples_per_image == 0, "M must be a multiple of samples_per_image");
+  HP3D_ARG(workspace_bytes >= hp3d_smpl_workspace_bytes(h, M, Mb), "workspace too small");
+  if (use_fused(h) && samples_per_image <= 112)      // chunk = image: statistics come out of the same kernel
+    return smpl_fused_forward(h->fused, betas, Mb, global_orient, Mg, body_pose, M, samples_per_image, vertices, joints, avg_dist,
+                              mean_vertices, workspace, (cudaStream_t)stream);
+  int rc = hp3d_smpl_forward(h, betas, Mb, global_orient, Mg, body_pose, M, vertices, joints, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  return hp3d_vertex_uncertainty(vertices, M / samples_per_image, samples_per_image, mean_vertices, avg_dist, stream);
 }
 
 extern "C" int hp3d_rodrigues(const float* aa, int n, float* R, void* stream) {

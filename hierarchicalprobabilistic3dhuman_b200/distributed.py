@@ -47,9 +47,21 @@ class SymmPush:
     all-reduce behind the copies: when it completes on a rank, every rank's preceding pushes have landed.
     `ok == False` (rendezvous unavailable) means: use `dist.all_gather_into_tensor` instead."""
 
-    def __init__(self, shape, device, rank, world, dtype=torch.float32):
+    def __init__(self, shape, device, rank, world, dtype=torch.float32, mode=None, ctas=None, fence_group=None):
+        import os
+        # `fence_group`: process group for the completion all-reduce. It must NOT be the group the caller uses for collectives
+        # on its main stream: ProcessGroupNCCL runs all collectives of a group on ONE internal stream, so a fence queued
+        # behind the pushes would hold up every later collective of that group -- and the stream that waits for it (this is
+        # what serialised the vertices gather with the next step's compute in round 1, whatever the transport).
+        self.fence_group = fence_group
+        # "kernel": hp3d_peer_push -- SM stores over NVLink from tiny CTAs that co-reside with the compute kernels (default);
+        # "ce": plain device-to-device copies on the copy engines (no SMs, but ~430 GB/s per rank measured at 4 GPUs)
+        # "mc": the same through the NVSwitch multicast mapping (one multimem.st reaches every GPU; falls back to "kernel"
+        # when the symmetric-memory handle has no multicast pointer)
+        self.mode = mode or os.environ.get("HP3D_PUSH", "mc")
+        self.ctas = int(ctas if ctas is not None else os.environ.get("HP3D_PUSH_CTAS", "0"))
         self.rank, self.world, self.ok, self.peers, self.error = rank, world, False, [], None
-        self.full = None
+        self.full, self.mc_ptr = None, 0
         good = 0.0
         try:
             import torch.distributed._symmetric_memory as symm_mem
@@ -57,12 +69,15 @@ class SymmPush:
             self.hdl = symm_mem.rendezvous(self.full, dist.group.WORLD)
             for r in range(world):
                 self.peers.append(None if r == rank else self.hdl.get_buffer(r, tuple(shape), dtype))
+            self.mc_ptr = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
             good = 1.0
         except Exception as e:           # noqa: BLE001 -- any failure means "use NCCL instead"
             self.error = repr(e)
-        ok = torch.full((1,), good, device=device)
+        ok = torch.tensor([good, 1.0 if self.mc_ptr else 0.0], device=device)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        self.ok = bool(ok.item() == 1)
+        self.ok = bool(ok[0].item() == 1)
+        if self.mode == "mc" and ok[1].item() != 1:
+            self.mode = "kernel"                    # no NVLS multicast mapping on some rank
         if not self.ok:
             self.peers = []
             if self.full is None:
@@ -77,6 +92,26 @@ class SymmPush:
         if not self.ok:
             return                                  # fallback mode: the caller gathers with NCCL / gloo
         src = view_fn(self.full)
+        if self.mode == "mc":
+            import ctypes
+            from . import _lib
+            assert src.is_contiguous()
+            off = src.data_ptr() - self.full.data_ptr()
+            with torch.cuda.device(self.full.device):
+                _lib.check(_lib.lib().hp3d_peer_push_multicast(src.data_ptr(), ctypes.c_void_p(self.mc_ptr + off),
+                                                               src.numel() * src.element_size(), self.ctas,
+                                                               ctypes.c_void_p(stream.cuda_stream)), "hp3d_peer_push_multicast")
+            return
+        if self.mode == "kernel":
+            import ctypes
+            from . import _lib
+            dsts = [view_fn(p) for p in self.peers if p is not None]
+            assert src.is_contiguous() and all(d.is_contiguous() for d in dsts)
+            arr = (ctypes.c_void_p * len(dsts))(*[d.data_ptr() for d in dsts])
+            with torch.cuda.device(self.full.device):
+                _lib.check(_lib.lib().hp3d_peer_push(src.data_ptr(), arr, len(dsts), src.numel() * src.element_size(), self.ctas,
+                                                     ctypes.c_void_p(stream.cuda_stream)), "hp3d_peer_push")
+            return
         if self._streams is None:
             self._streams = [torch.cuda.Stream(device=self.full.device) for _ in range(self.num_streams)]
         start = torch.cuda.Event()
@@ -104,4 +139,4 @@ class SymmPush:
 
     def fence(self, stream):
         with torch.cuda.stream(stream):
-            dist.all_reduce(self.flag)
+            dist.all_reduce(self.flag, group=self.fence_group)

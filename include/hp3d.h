@@ -61,7 +61,21 @@ size_t hp3d_smpl_workspace_bytes(const hp3d_smpl* h, int M, int Mb);
 int hp3d_smpl_forward(const hp3d_smpl* h, const float* betas, int Mb, const float* global_orient, int Mg,
                       const float* body_pose, int M, float* vertices, float* joints,
                       void* workspace, size_t workspace_bytes, void* stream);
-/* stage-level entry points (used by tests / profiling; hp3d_smpl_forward = these three in order) */
+/* hp3d_smpl_forward for B images x N samples (M = B * samples_per_image, image-major) that ALSO returns the per-vertex
+ * statistics of utils/sampling_utils.py:189-190 per image: avg_dist [B*6890] = mean over the image's samples of the
+ * distance to the image's mean mesh, mean_vertices [B*6890*3] (may be NULL). With the default fused kernel and
+ * samples_per_image <= 112 the statistics come out of the SMPL kernel itself (the sample vertices are never re-read from
+ * HBM); otherwise it is hp3d_smpl_forward followed by hp3d_vertex_uncertainty. */
+int hp3d_smpl_forward_stats(const hp3d_smpl* h, const float* betas, int Mb, const float* global_orient, int Mg,
+                            const float* body_pose, int M, int samples_per_image, float* vertices, float* joints,
+                            float* avg_dist, float* mean_vertices, void* workspace, size_t workspace_bytes, void* stream);
+/* which path a handle takes (fused = 1 unless HP3D_SMPL=staged or no tensor-map support), whether its vertices were
+ * re-ordered by dominant joint at create time, and the sum / maximum over the 216 32-vertex tiles of distinct skinning
+ * joints (the fused kernel's skinning cost is proportional to the sum). */
+int hp3d_smpl_layout_info(const hp3d_smpl* h, int* fused, int* permuted, int* tile_joint_sum, int* tile_joint_max);
+/* stage-level entry points of the STAGED path (HP3D_SMPL=staged; used by tests / profiling; the staged hp3d_smpl_forward =
+ * these three in order). The default hp3d_smpl_forward is ONE fused tensor-core kernel (csrc/smpl_fused.cu): v_posed never
+ * exists in memory. */
 int hp3d_smpl_shape_blend(const hp3d_smpl* h, const float* betas, int Mb, float* v_shaped /*[Mb*20672]*/,
                           float* J /*[Mb*24*3]*/, void* stream);
 size_t hp3d_smpl_pose_blend_workspace_bytes(int M);   /* fp16 hi/lo pose features for the tensor-core blend */
@@ -218,6 +232,19 @@ int hp3d_encoder_forward_image(const hp3d_encoder* h, const float* rgb, const fl
  * per-layer kernels against models/resnet.py:203-212; taps == NULL behaves like hp3d_encoder_forward). */
 int hp3d_encoder_forward_taps(const hp3d_encoder* h, const float* x_nchw, int B, int H, int W, float* feats,
                               void* workspace, size_t workspace_bytes, float* taps, void* stream);
+
+/* ---------------------------------------------------------------- multi-GPU gather by peer stores
+ * New (the reference has no distributed code). Copies `bytes` (a multiple of 16) from `src` to each of the
+ * `n_peers` (<= 15) destination pointers -- the same slice of every peer's gather buffer, mapped into this process through
+ * CUDA peer / symmetric memory -- with a grid of `ctas` (<= 0: default) 128-thread, no-shared-memory CTAs that are small
+ * enough to run NEXT TO the hot path's kernels on the same SMs, so the NVLink transfer of chunk c overlaps the kernels of
+ * chunk c + 1 (NCCL's all-gather kernels cannot: DESIGN.md 6). Ends with a system-scope fence; the caller exchanges a
+ * completion flag afterwards. */
+int hp3d_peer_push(const void* src, void* const* peer_dsts, int n_peers, size_t bytes, int ctas, void* stream);
+/* The same through an NVSwitch multicast (NVLS) address of the gather buffer: `multicast_dst` is the slice's address in the
+ * multicast mapping (torch symmetric memory: handle.multicast_ptr + byte offset); one multimem.st reaches every GPU of the
+ * group, so the slice leaves this GPU once instead of (world - 1) times. */
+int hp3d_peer_push_multicast(const void* src, void* multicast_dst, size_t bytes, int ctas, void* stream);
 
 #ifdef __cplusplus
 }
