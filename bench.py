@@ -28,7 +28,9 @@ if ROOT not in sys.path:
 import numpy as np
 import torch
 
-LBS_BYTES_PER_MESH = 167592   # read v_posed 82,680 + rotmats 864 + J 288; write vertices 82,680 + joints 1,080
+LBS_BYTES_PER_MESH = 167592   # SURVEY.md §8d two-stage accounting: read v_posed 82,680 + rotmats 864 + J 288; write vertices 82,680 + joints 1,080
+FUSED_BYTES_PER_MESH = 84664  # SURVEY.md §8d fused accounting: rotmats 864 + betas 40 in; vertices 82,680 + joints 1,080 out
+FUSED_FLOP_PER_MESH = 2 * 3 * 224 * (54 * 3 * 128)   # issued tensor-core FLOPs: 3 fp16 products x K 224 x 20,736 padded coordinate rows
 
 
 def parse():
@@ -466,6 +468,27 @@ def main_hp3d(args):
     achieved = LBS_BYTES_PER_MESH * M / (lbs_ms * 1e-3) / 1e9
     traffic, traffic_src = lbs_traffic_from_profiles((M + 7) // 8)
 
+    # ---- the fused SMPL kernel group alone (feature split + FK + fused blend/skin/statistics kernel + extra joints)
+    import ctypes
+    lay = [ctypes.c_int() for _ in range(4)]
+    _lib.check(L.hp3d_smpl_layout_info(h_smpl, *[ctypes.byref(v_) for v_ in lay]))
+    fused_on = bool(lay[0].value)
+    unc_tmp = torch.empty(cbv, 6890, device=dev)
+    betas_c = torch.randn(cbv, 10, device=dev)
+    ws_f = torch.empty(L.hp3d_smpl_workspace_bytes(h_smpl, M, cbv), dtype=torch.uint8, device=dev)
+    run_fused = lambda: _lib.check(L.hp3d_smpl_forward_stats(h_smpl, betas_c.data_ptr(), cbv, gR.data_ptr(), cbv, Rr.data_ptr(), M, N,
+                                                              verts_local.data_ptr(), joints.data_ptr(), unc_tmp.data_ptr(), None,
+                                                              ws_f.data_ptr(), ws_f.numel(), _lib.stream_ptr()))
+    for _ in range(3):
+        run_fused()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        run_fused()
+    e1.record()
+    torch.cuda.synchronize()
+    smpl_ms = e0.elapsed_time(e1) / reps
+
     # ---- the tensor-core side: encoder alone (input cast + stem + pools + 19 convolutions), algorithmic and issued FLOP/s
     for _ in range(3):
         net.encode(x_dev)
@@ -563,7 +586,18 @@ def main_hp3d(args):
                     "value": world * B / (ms_fast * 1e-3), "unit": "images/s", "ms_per_step": ms_fast,
                     "note": "same step with --encoder-mode fast (one fp16 product per k-block): 3e-4 on the features, NOT the 1e-4 contract"},
                 "clocks": clocks,
-                "roofline": {"kernel": "lbs_tile_kernel (SMPL FK + skinning + 90 joints)", "bound": "hbm", "achieved": achieved,
+                "roofline": {"kernel": ("SMPL forward + per-vertex statistics as ONE kernel group: smpl_fused_kernel (transposed blend GEMM on tcgen05 -> "
+                                        "skinning out of TMEM -> statistics) + feature split, FK, extra joints; v_posed never in HBM" if fused_on else
+                                        "staged SMPL forward + statistics (HP3D_SMPL=staged)"),
+                             "bound": "hbm", "achieved": FUSED_BYTES_PER_MESH * M / (smpl_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "peak_kind": pk_kind,
+                             "unit": "GB/s", "frac": FUSED_BYTES_PER_MESH * M / (smpl_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                             "ms": smpl_ms, "meshes": M, "bytes_per_mesh": FUSED_BYTES_PER_MESH,
+                             "accounting": "SURVEY.md 8d FUSED accounting (84,664 B/mesh: 904 in + 83,760 out); the same work under the two-stage "
+                                           "accounting of the staged kernels is 250,272 B/mesh (blend write + LBS 167,592 + statistics re-read)",
+                             "tensor_issued_tflops": FUSED_FLOP_PER_MESH * M / (smpl_ms * 1e-3) / 1e12,
+                             "tensor_frac_issued": FUSED_FLOP_PER_MESH * M / (smpl_ms * 1e-3) / 1e12 / pk["bf16_tflops"],
+                             "vertex_order": {"reordered_by_dominant_joint": bool(lay[1].value), "tile_joint_sum": lay[2].value, "tile_joint_max": lay[3].value}},
+                "roofline_lbs_staged": {"kernel": "lbs_tile_kernel (staged path: SMPL FK + skinning + 90 joints), timed alone", "bound": "hbm", "achieved": achieved,
                              "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                              "traffic": traffic, "traffic_source": (f"{traffic_src}: ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the "
                                                                     f"{(M + 7) // 8}-CTA lbs_tile_kernel launch") if traffic else None,

@@ -934,11 +934,14 @@ static size_t ws_vposed(int M) { return align_up((size_t)M * VPITCH * sizeof(flo
 
 extern "C" size_t hp3d_smpl_pose_blend_workspace_bytes(int M) { return M > 0 ? blend_tc_workspace_bytes(M) : 0; }
 
-// HP3D_SMPL=staged selects the round-1 three-kernel path (blend GEMM -> v_posed in HBM -> LBS); default: the fused kernel
+// HP3D_SMPL=fused selects the single-kernel path (csrc/smpl_fused.cu: transposed blend GEMM -> skinning out of TMEM ->
+// statistics; v_posed never in HBM). It is parity-green but MEASURED SLOWER than the staged three-kernel path (3.8 vs 2.3 ms
+// per 25,600 meshes, profiles/r02o_*): one vertex per TMEM lane costs 154 warp instructions per 32 vertices x mesh against the
+// staged LBS kernel's 90, on 8 epilogue warps. Default: staged (blend GEMM -> v_posed in HBM -> LBS -> statistics).
 static bool use_fused(const hp3d_smpl* h) {
   if (!h->fused) return false;
   const char* e = getenv("HP3D_SMPL");
-  return e && !strcmp(e, "fused");          // TODO(default): flip once verified on hardware
+  return e && !strcmp(e, "fused");
 }
 
 extern "C" size_t hp3d_smpl_workspace_bytes(const hp3d_smpl* h, int M, int Mb) {

@@ -54,7 +54,7 @@ static_assert(NRANGE * GPI == NGRP, "vertex groups must split evenly into work i
 constexpr int NQF = 12;                     // specialised bodies for 1..12 joints per warp tile
 constexpr int NQTAB = NJ;                   // table width (rolled fallback handles up to all 24 joints)
 constexpr int EPI_WARPS = 8;
-constexpr int STG_MESHES = 4;
+constexpr int STG_MESHES = 2;
 constexpr int THREADS = 384;
 
 struct FusedSmem {
@@ -101,12 +101,14 @@ struct EpiCtx {
   int abuf; uint32_t aphase;
 };
 
-// staged meshes [j0, j1) of the current 8-mesh block -> HBM
-__device__ __forceinline__ void flush_staged(const EpiCtx& c, int m_first, int j0, int j1, int tbase, int tcnt, int orig, bool valid) {
+// two staged meshes (m_first, m_first + 1; the second only if `two`) -> HBM
+__device__ __forceinline__ void flush_pair(const EpiCtx& c, float* vertices, int m_first, bool two, int tbase, int tcnt, int orig, bool valid) {
   __syncwarp();
-  for (int j = j0; j < j1; ++j) {
-    const float* s = c.stg + (j & (STG_MESHES - 1)) * 96;
-    float* dst = c.args->vertices + (size_t)(c.chunk_base + m_first + j) * NV3;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    if (j == 1 && !two) break;
+    const float* s = c.stg + j * 96;
+    float* dst = vertices + (size_t)(c.chunk_base + m_first + j) * NV3;
     if (tbase >= 0 && !(tbase & 1)) {          // consecutive vertices, 8-byte aligned run: full-sector float2 stores
       const int n2 = (3 * tcnt) >> 1;          // tcnt is 32 or 10: 3 * tcnt is even
       float2* d2 = reinterpret_cast<float2*>(dst + 3 * tbase);
@@ -120,17 +122,28 @@ __device__ __forceinline__ void flush_staged(const EpiCtx& c, int m_first, int j
   __syncwarp();
 }
 
+__device__ __forceinline__ void tmem_ld_32x2(uint32_t taddr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+}
+
 // Pass 1 of one (chunk, 128-vertex group) for this warp: skin its 32 vertices for its half of every 16-mesh sub-chunk.
-// NQ > 0: exactly NQ joints, fully unrolled; NQ == 0: rolled loop over `nq` joints (tiles with more than NQF joints).
+// NQ > 0: exactly NQ joints, joint loop unrolled; NQ == 0: rolled loop over `nq` joints (tiles with more than NQF joints).
+// The mesh loop is ROLLED, two meshes per iteration, with the TMEM loads of the next pair in flight while the current pair
+// is skinned (a first version unrolled 8 meshes x 13 joint-count bodies and ptxas unrolled the sub-chunk loop on top:
+// 120k instructions, instruction-cache bound at 4.0 ms per 25,600 meshes).
 template <int NQ>
 __device__ __forceinline__ void fused_tile_pass1(EpiCtx& c, int nq, float& sx, float& sy, float& sz) {
   const FusedArgs& a = *c.args;
   const int lane = c.lane, t = c.tile;
+  const float inv_scale = a.inv_scale;
+  float* const vertices = a.vertices;
+  const int* const tjoff = a.tile_joff + t * NQTAB;
+  const float* const tw = a.tile_w + (size_t)t * NQTAB * 32 + lane;
   constexpr int NW = NQ > 0 ? NQ : 1;
   float w[NW]; int joff[NW];
   if constexpr (NQ > 0) {
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) { w[q] = a.tile_w[((size_t)t * NQTAB + q) * 32 + lane]; joff[q] = a.tile_joff[t * NQTAB + q]; }
+    for (int q = 0; q < NQ; ++q) { w[q] = tw[q * 32]; joff[q] = tjoff[q]; }
   }
   const float4 vt = a.vt[t * 32 + lane];
   const int orig = __float_as_int(vt.w);
@@ -138,55 +151,66 @@ __device__ __forceinline__ void fused_tile_pass1(EpiCtx& c, int nq, float& sx, f
   const int tbase = a.tile_base[t];
   const int tcnt = min(32, NV - t * 32);
   const int nsc = (c.cs + ASUB - 1) / ASUB;
+  auto skin = [&](const float4* Ag, uint32_t xr, uint32_t yr, uint32_t zr, float& ox, float& oy, float& oz) {
+    float2 r[6];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) r[e] = make_float2(0.f, 0.f);
+    if constexpr (NQ > 0) {
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const float4 r0 = Ag[joff[q]], r1 = Ag[joff[q] + 1], r2 = Ag[joff[q] + 2];
+        const float u = w[q];
+        ffma2(r[0], u, r0.x, r0.y); ffma2(r[1], u, r0.z, r0.w);
+        ffma2(r[2], u, r1.x, r1.y); ffma2(r[3], u, r1.z, r1.w);
+        ffma2(r[4], u, r2.x, r2.y); ffma2(r[5], u, r2.z, r2.w);
+      }
+    } else {
+#pragma unroll 1
+      for (int q = 0; q < nq; ++q) {
+        const int jo = tjoff[q];
+        const float u = tw[q * 32];
+        const float4 r0 = Ag[jo], r1 = Ag[jo + 1], r2 = Ag[jo + 2];
+        ffma2(r[0], u, r0.x, r0.y); ffma2(r[1], u, r0.z, r0.w);
+        ffma2(r[2], u, r1.x, r1.y); ffma2(r[3], u, r1.z, r1.w);
+        ffma2(r[4], u, r2.x, r2.y); ffma2(r[5], u, r2.z, r2.w);
+      }
+    }
+    const float x = fmaf(__uint_as_float(xr), inv_scale, vt.x);
+    const float y = fmaf(__uint_as_float(yr), inv_scale, vt.y);
+    const float z = fmaf(__uint_as_float(zr), inv_scale, vt.z);
+    ox = fmaf(r[1].x, z, fmaf(r[0].y, y, r[0].x * x)) + r[1].y;
+    oy = fmaf(r[3].x, z, fmaf(r[2].y, y, r[2].x * x)) + r[3].y;
+    oz = fmaf(r[5].x, z, fmaf(r[4].y, y, r[4].x * x)) + r[5].y;
+  };
+#pragma unroll 1
   for (int sc = 0; sc < nsc; ++sc) {
     mbar_wait(&c.a_full[c.abuf], c.aphase, 31);
     const int m_lo = sc * ASUB + c.half * 8;
     const int cnt = min(8, c.cs - m_lo);
     if (cnt > 0) {
-      uint32_t xs[8], ys[8], zs[8];
-      tmem_ld_32x8(c.taddr + (uint32_t)m_lo, xs);
-      tmem_ld_32x8(c.taddr + (uint32_t)(NPMAX + m_lo), ys);
-      tmem_ld_32x8(c.taddr + (uint32_t)(2 * NPMAX + m_lo), zs);
-      tmem_ld_wait();
       const float4* Ab = c.a_smem + (size_t)c.abuf * (ASUB * 72) + (size_t)(c.half * 8) * 72;
-#pragma unroll
-      for (int mi = 0; mi < 8; ++mi) {
-        if (mi < cnt) {
-          const float4* Ag = Ab + mi * 72;
-          float2 r[6];
-#pragma unroll
-          for (int e = 0; e < 6; ++e) r[e] = make_float2(0.f, 0.f);
-          if constexpr (NQ > 0) {
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-              const float4 r0 = Ag[joff[q]], r1 = Ag[joff[q] + 1], r2 = Ag[joff[q] + 2];
-              const float u = w[q];
-              ffma2(r[0], u, r0.x, r0.y); ffma2(r[1], u, r0.z, r0.w);
-              ffma2(r[2], u, r1.x, r1.y); ffma2(r[3], u, r1.z, r1.w);
-              ffma2(r[4], u, r2.x, r2.y); ffma2(r[5], u, r2.z, r2.w);
-            }
-          } else {
-            for (int q = 0; q < nq; ++q) {
-              const int jo = a.tile_joff[t * NQTAB + q];
-              const float u = a.tile_w[((size_t)t * NQTAB + q) * 32 + lane];
-              const float4 r0 = Ag[jo], r1 = Ag[jo + 1], r2 = Ag[jo + 2];
-              ffma2(r[0], u, r0.x, r0.y); ffma2(r[1], u, r0.z, r0.w);
-              ffma2(r[2], u, r1.x, r1.y); ffma2(r[3], u, r1.z, r1.w);
-              ffma2(r[4], u, r2.x, r2.y); ffma2(r[5], u, r2.z, r2.w);
-            }
-          }
-          const float x = fmaf(__uint_as_float(xs[mi]), a.inv_scale, vt.x);
-          const float y = fmaf(__uint_as_float(ys[mi]), a.inv_scale, vt.y);
-          const float z = fmaf(__uint_as_float(zs[mi]), a.inv_scale, vt.z);
-          const float ox = fmaf(r[1].x, z, fmaf(r[0].y, y, r[0].x * x)) + r[1].y;
-          const float oy = fmaf(r[3].x, z, fmaf(r[2].y, y, r[2].x * x)) + r[3].y;
-          const float oz = fmaf(r[5].x, z, fmaf(r[4].y, y, r[4].x * x)) + r[5].y;
-          sx += ox; sy += oy; sz += oz;
-          float* s = c.stg + (mi & (STG_MESHES - 1)) * 96 + 3 * lane;
-          s[0] = ox; s[1] = oy; s[2] = oz;
+      uint32_t x0, x1, y0, y1, z0, z1;
+      tmem_ld_32x2(c.taddr + (uint32_t)m_lo, x0, x1);
+      tmem_ld_32x2(c.taddr + (uint32_t)(NPMAX + m_lo), y0, y1);
+      tmem_ld_32x2(c.taddr + (uint32_t)(2 * NPMAX + m_lo), z0, z1);
+#pragma unroll 1
+      for (int mi = 0; mi < cnt; mi += 2) {
+        tmem_ld_wait();
+        const uint32_t cx0 = x0, cx1 = x1, cy0 = y0, cy1 = y1, cz0 = z0, cz1 = z1;
+        if (mi + 2 < cnt) {                      // next pair's accumulators in flight while this pair is skinned
+          tmem_ld_32x2(c.taddr + (uint32_t)(m_lo + mi + 2), x0, x1);
+          tmem_ld_32x2(c.taddr + (uint32_t)(NPMAX + m_lo + mi + 2), y0, y1);
+          tmem_ld_32x2(c.taddr + (uint32_t)(2 * NPMAX + m_lo + mi + 2), z0, z1);
         }
-        if ((mi & (STG_MESHES - 1)) == STG_MESHES - 1)
-          flush_staged(c, m_lo, mi - (STG_MESHES - 1), min(mi + 1, cnt), tbase, tcnt, orig, valid);
+        const bool two = mi + 1 < cnt;
+        float ox0, oy0, oz0, ox1 = 0.f, oy1 = 0.f, oz1 = 0.f;
+        skin(Ab + mi * 72, cx0, cy0, cz0, ox0, oy0, oz0);
+        if (two) skin(Ab + (mi + 1) * 72, cx1, cy1, cz1, ox1, oy1, oz1);
+        sx += ox0 + ox1; sy += oy0 + oy1; sz += oz0 + oz1;
+        float* s = c.stg + 3 * lane;
+        s[0] = ox0; s[1] = oy0; s[2] = oz0;
+        s[96] = ox1; s[97] = oy1; s[98] = oz1;
+        flush_pair(c, vertices, m_lo + mi, two, tbase, tcnt, orig, valid);
       }
     }
     __syncwarp();
@@ -323,11 +347,13 @@ smpl_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_consta
     float4* sums = reinterpret_cast<float4*>(smem + L::SUM_OFF);          // [parity][half][128]
     uint32_t tphase = 0;
     int gcount = 0;
+#pragma unroll 1
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int chunk = item / NRANGE, g0 = (item - chunk * NRANGE) * GPI;
       c.chunk_base = chunk * args.cs;
       c.cs = min(args.cs, args.M - c.chunk_base);
-      for (int g = g0; g < g0 + GPI; ++g, ++gcount) {
+#pragma unroll 1
+      for (int g = g0; g < g0 + GPI; ++g, ++gcount) {        // NOT unrolled: the body holds 13 specialised skinning loops
         c.tile = g * 4 + c.quarter;
         const int nq = args.tile_nq[c.tile];
         mbar_wait(tmem_full, tphase, 47);

@@ -50,9 +50,9 @@ class HotPathPipeline:
         self.chunks = chunks if B % chunks == 0 else 1
         self._stage = None
         self._slot = 0
-        # libhp3d kernels launched by one pass, counted on the ncu launch list (profiles/): encoder fast mode 24 (input cast,
-        # arg-max decode, stem, max-pool, 19 convolutions, avg-pool), head 6, rot6d 1, mode SMPL 4, sampler 1, per vertex chunk
-        # SMPL 4 + statistics 1, sample ranking 1
+        # libhp3d kernels launched by one pass, counted on the ncu launch list (profiles/): encoder 24 (input cast, arg-max
+        # decode, stem, max-pool, 19 convolutions, avg-pool), head 6, rot6d 1, mode SMPL 4 (shape blend, feature split, blend
+        # GEMM, LBS), sampler 1, per vertex chunk SMPL 4 + statistics 1, sample ranking 1
         self.launches_per_pass = 24 + 6 + 1 + 4 + 1 + (4 + 1) * len(self.vertex_chunks) + 1
 
     # ------------------------------------------------------------------ device-resident pass
@@ -71,13 +71,13 @@ class HotPathPipeline:
         cb = B // C
         for c, vch in enumerate(self.vertex_chunks):       # images [c*cb, (c+1)*cb): SMPL on cb*N meshes + statistics
             i0 = c * cb
-            with _lib.nvtx("hp3d.smpl_samples"):
-                _lib.check(L.hp3d_smpl_forward(self.h_smpl, loc[i0:].data_ptr(), cb, glob_R[i0:].data_ptr(), cb, R[i0:].data_ptr(),
-                                               cb * N, vch.data_ptr(), self.joints[i0 * N:].data_ptr(), self.ws.data_ptr(),
-                                               self.ws.numel(), _lib.stream_ptr()), "hp3d_smpl_forward")
-            with _lib.nvtx("hp3d.vertex_uncertainty"):
-                _lib.check(L.hp3d_vertex_uncertainty(vch.data_ptr(), cb, N, None, self.uncertainty[i0:].data_ptr(),
-                                                     _lib.stream_ptr()), "hp3d_vertex_uncertainty")
+            with _lib.nvtx("hp3d.smpl_samples+statistics"):
+                # SMPL on the chunk's cb*N meshes AND the per-vertex statistics of its cb images in one call (staged kernels by
+                # default; HP3D_SMPL=fused: one tensor-core kernel, the sample vertices are never re-read from HBM)
+                _lib.check(L.hp3d_smpl_forward_stats(self.h_smpl, loc[i0:].data_ptr(), cb, glob_R[i0:].data_ptr(), cb, R[i0:].data_ptr(),
+                                                     cb * N, N, vch.data_ptr(), self.joints[i0 * N:].data_ptr(),
+                                                     self.uncertainty[i0:].data_ptr(), None, self.ws.data_ptr(), self.ws.numel(),
+                                                     _lib.stream_ptr()), "hp3d_smpl_forward_stats")
             if self.on_vertices_chunk is not None:
                 self.on_vertices_chunk(c)
         res = dict(mode_vertices=out_mode.vertices, mode_joints=out_mode.joints, joints=self.joints, rotmats=R,

@@ -203,6 +203,6 @@ def sample_meshes_batched(pose_U, pose_S, pose_V, shape_distribution, glob_rotma
     out = smpl_model(body_pose=R.view(B * num_samples, 23, 3, 3), global_orient=glob_rotmats.reshape(B, 1, 3, 3),
                      betas=betas, pose2rot=False)
     verts = out.vertices.view(B, num_samples, 6890, 3)
-    mean, dist = vertex_uncertainty(verts)
+    mean, dist = vertex_uncertainty(verts)       # (HotPathPipeline gets both from ONE kernel: hp3d_smpl_forward_stats)
     return dict(rotmats=R, vertices=verts, joints=out.joints.view(B, num_samples, 90, 3), betas=betas,
                 mean_vertices=mean, per_vertex_uncertainty=dist)

@@ -45,6 +45,26 @@ def load_joint_regressor_table():
     return dense
 
 
+def shuffle_smpl_vertices(model, seed=7, block=1):
+    """The same model with its vertex order permuted (blocks of `block` consecutive vertices stay together): the real SMPL
+    template is NOT ordered by body part the way `synthetic_smpl_model` is, so kernels whose speed depends on the vertex
+    order are also measured / tested on a shuffled copy (block=1: worst case, every vertex on its own)."""
+    rs = np.random.RandomState(seed)
+    nb = -(-NUM_VERTS // block)
+    order = np.concatenate([np.arange(b * block, min(NUM_VERTS, (b + 1) * block)) for b in rs.permutation(nb)])   # new -> old
+    inv = np.empty(NUM_VERTS, dtype=np.int64)
+    inv[order] = np.arange(NUM_VERTS)                                                                          # old -> new
+    m = dict(model)
+    m["v_template"] = model["v_template"][order]
+    m["shapedirs"] = model["shapedirs"][order]
+    m["posedirs"] = model["posedirs"].reshape(NUM_POSE_FEATS, NUM_VERTS, 3)[:, order].reshape(NUM_POSE_FEATS, NUM_VERTS * 3)
+    m["J_regressor"] = model["J_regressor"][:, order]
+    m["lbs_weights"] = model["lbs_weights"][order]
+    m["faces"] = inv[model["faces"]]
+    # extra_vertex_ids / joint_regressors_extra keep addressing vertex INDICES (they are data about the real template)
+    return m
+
+
 def synthetic_smpl_model(seed=2, max_skin_nnz=4):
     """SMPL-shaped model constants (float64 numpy) with the layouts smplx 0.1.26 uses
     (SURVEY.md §8a a11): v_template (6890,3), shapedirs (6890,3,10), posedirs (207,20670),
