@@ -74,8 +74,8 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
-def lbs_traffic_from_profiles(grid_ctas):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the LBS launch with `grid_ctas` CTAs from the newest committed
+def traffic_from_profiles(kernel, grid_ctas):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the launch of `kernel` with `grid_ctas` CTAs from the newest committed
     `ncu --set full` summary under profiles/ (tools/ncu_summary.py export), or (None, None)."""
     import csv, glob
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_summary.csv")), reverse=True):
@@ -85,7 +85,7 @@ def lbs_traffic_from_profiles(grid_ctas):
             ki, gi, ri, wi = hdr.index("Kernel Name"), hdr.index("Grid Size"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
             unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(rows[1][ri], 1e9)
             for r in rows[2:]:
-                if "lbs_tile_kernel" in r[ki] and r[gi].replace(" ", "").startswith(f"({grid_ctas},"):
+                if kernel in r[ki] and r[gi].replace(" ", "").startswith(f"({grid_ctas},"):
                     return (float(r[ri]) + float(r[wi])) * unit, os.path.relpath(path, ROOT)
         except Exception:
             continue
@@ -466,7 +466,8 @@ def main_hp3d(args):
     lbs_ms = e0.elapsed_time(e1) / reps
     pk, pk_kind = peaks()
     achieved = LBS_BYTES_PER_MESH * M / (lbs_ms * 1e-3) / 1e9
-    traffic, traffic_src = lbs_traffic_from_profiles((M + 7) // 8)
+    traffic, traffic_src = traffic_from_profiles("lbs_tile_kernel", (M + 7) // 8)
+    ftraffic, ftraffic_src = traffic_from_profiles("smpl_fused_kernel", min(148, (M // N) * 9))
 
     # ---- the fused SMPL kernel group alone (feature split + FK + fused blend/skin/statistics kernel + extra joints)
     import ctypes
@@ -521,7 +522,7 @@ def main_hp3d(args):
 
     # ---- N == 1: end to end INCLUDING the sampled vertices (2.12 GB/step of D2H)
     ms_full = None
-    if world == 1 and pipe.vertices is not None:
+    if world == 1 and (pipe.vertices is not None or len(pipe.vertex_chunks) == 1):
         nfull = max(2, min(args.steps, 4))
         last = pipe.run_host(x_hosts[0], return_vertices=True)
         last[1].synchronize()
@@ -590,7 +591,12 @@ def main_hp3d(args):
                                         "skinning out of TMEM -> statistics) + feature split, FK, extra joints; v_posed never in HBM" if fused_on else
                                         "staged SMPL forward + statistics (HP3D_SMPL=staged)"),
                              "bound": "hbm", "achieved": FUSED_BYTES_PER_MESH * M / (smpl_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "peak_kind": pk_kind,
-                             "unit": "GB/s", "frac": FUSED_BYTES_PER_MESH * M / (smpl_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                             "unit": "GB/s", "frac": FUSED_BYTES_PER_MESH * M / (smpl_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                             "traffic": ftraffic, "traffic_source": (f"{ftraffic_src}: ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the "
+                                                                     "smpl_fused_kernel launch") if ftraffic else None,
+                             "limiter": "not HBM: the kernel's DRAM traffic equals its algorithmic bytes, but per (image, 128-vertex group) the blend MMAs "
+                                        "(posedirs streamed L2 -> smem through a 48 KB TMA ring: in-flight bytes, not bandwidth) and the skinning phase "
+                                        "run back to back because 336 + 96 of the 512 TMEM columns leave no second blend accumulator (profiles/README.md)",
                              "ms": smpl_ms, "meshes": M, "bytes_per_mesh": FUSED_BYTES_PER_MESH,
                              "accounting": "SURVEY.md 8d FUSED accounting (84,664 B/mesh: 904 in + 83,760 out); the same work under the two-stage "
                                            "accounting of the staged kernels is 250,272 B/mesh (blend write + LBS 167,592 + statistics re-read)",

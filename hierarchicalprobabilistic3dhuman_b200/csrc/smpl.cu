@@ -934,14 +934,15 @@ static size_t ws_vposed(int M) { return align_up((size_t)M * VPITCH * sizeof(flo
 
 extern "C" size_t hp3d_smpl_pose_blend_workspace_bytes(int M) { return M > 0 ? blend_tc_workspace_bytes(M) : 0; }
 
-// HP3D_SMPL=fused selects the single-kernel path (csrc/smpl_fused.cu: transposed blend GEMM -> skinning out of TMEM ->
-// statistics; v_posed never in HBM). It is parity-green but MEASURED SLOWER than the staged three-kernel path (3.8 vs 2.3 ms
-// per 25,600 meshes, profiles/r02o_*): one vertex per TMEM lane costs 154 warp instructions per 32 vertices x mesh against the
-// staged LBS kernel's 90, on 8 epilogue warps. Default: staged (blend GEMM -> v_posed in HBM -> LBS -> statistics).
+// Default: the fused kernel (csrc/smpl_fused.cu: transposed blend GEMM -> tensor-core skinning -> statistics; v_posed never
+// in HBM; speed independent of the model's vertex order). HP3D_SMPL=staged selects the round-1 three-kernel path (blend GEMM
+// -> v_posed in HBM -> lbs_tile_kernel / generic lbs_kernel -> statistics kernel), kept for comparison and as the path for
+// hosts without cuTensorMapEncodeTiled. Measured per 25,600 meshes incl. statistics (profiles/r02r_bench_smpl.jsonl):
+// fused 2.25 ms on any vertex order; staged 2.32 ms part-ordered, 3.84 ms shuffled.
 static bool use_fused(const hp3d_smpl* h) {
   if (!h->fused) return false;
   const char* e = getenv("HP3D_SMPL");
-  return e && !strcmp(e, "fused");
+  return !(e && !strcmp(e, "staged"));
 }
 
 extern "C" size_t hp3d_smpl_workspace_bytes(const hp3d_smpl* h, int M, int Mb) {
@@ -1054,7 +1055,7 @@ extern "C" int hp3d_smpl_forward_stats(const hp3d_smpl* h, const float* betas, i
   HP3D_ARG(M > 0 && Mb > 0 && Mg > 0 && M % Mb == 0 && M % Mg == 0, "M must be a multiple of Mb and Mg");
   HP3D_ARG(samples_per_image > 0 && M % samples_per_image == 0, "M must be a multiple of samples_per_image");
   HP3D_ARG(workspace_bytes >= hp3d_smpl_workspace_bytes(h, M, Mb), "workspace too small");
-  if (use_fused(h) && samples_per_image <= 112)      // chunk = image: statistics come out of the same kernel
+  if (use_fused(h) && samples_per_image <= 112 && samples_per_image >= 8)      // chunk = image: statistics come out of the same kernel
     return smpl_fused_forward(h->fused, betas, Mb, global_orient, Mg, body_pose, M, samples_per_image, vertices, joints, avg_dist,
                               mean_vertices, workspace, (cudaStream_t)stream);
   int rc = hp3d_smpl_forward(h, betas, Mb, global_orient, Mg, body_pose, M, vertices, joints, workspace, workspace_bytes, stream);

@@ -12,14 +12,21 @@
 //     accumulators side by side give every TMEM lane (= thread of the epilogue) the x, y, z of ONE vertex for every mesh of
 //     the chunk: exactly the layout skinning wants (lane = vertex, loop over meshes, joint transforms broadcast from
 //     shared memory, per-lane weights in registers) -- no transpose, no shared-memory staging of v_posed;
+//   * SKINNING is a second tensor-core contraction: T[vertex][(mesh, 3x4)] = W[vertex][joint] x A[(mesh, 3x4)][joint]^T
+//     (K = 24 joints, fp16 hi/lo pairs, three products) -- what smplx itself computes as a dense matmul. Four meshes at a
+//     time (N = 48) it lands in a double-buffered TMEM accumulator NEXT to the blend accumulators, lane = the same vertex,
+//     so the epilogue is 12 FMAs per (vertex, mesh): out = T[:, :3] v_posed + T[:, 3]. (A first version blended the joint
+//     transforms on the CUDA cores like lbs_tile_kernel: 154 warp instructions per 32 vertices x mesh on 8 epilogue warps,
+//     3.8 ms per 25,600 meshes against 2.3 ms staged -- profiles/r02o_fused_ncu.md.) W (per 128-vertex group) and A^T (per 8
+//     meshes, written by smpl_fk_kernel) are stored in HBM directly in the UMMA no-swizzle K-major core-matrix order, so
+//     plain 1-D bulk copies stage them;
 //   * a work item = one chunk of <= 112 meshes (the N samples of an image) x 6 vertex groups: the chunk's features stay
-//     resident in shared memory (112 KB), the posedirs planes stream through a TMA ring, the per-mesh skinning transforms
-//     A (24 x 3x4, from smpl_fk_kernel) stream in 16-mesh sub-chunks through a second ring;
-//   * 8 epilogue warps: warp = (TMEM lane quarter, mesh half). Per 32-vertex warp tile the distinct joints are listed at
-//     create time (vertices are re-ordered by dominant joint when that shortens the lists, so ANY weight layout gets short
-//     lists; tiles with more than 12 joints take a rolled loop -- a per-tile, never a global, fallback) and the body is
-//     specialised per joint count like lbs_tile_kernel. Skinned vertices leave through a 1.5 KB per-warp staging buffer as
-//     full-sector 8-byte stores (one vertex per lane would otherwise write 4-byte pieces at a 12-byte stride);
+//     resident in shared memory (112 KB), the posedirs planes stream through a TMA ring;
+//   * 8 epilogue warps: warp = (TMEM lane quarter, half); a half owns one of the two T accumulators, i.e. every other
+//     4-mesh sub-chunk. Vertices may be re-ordered at create time (a hook for
+//     layouts whose order scatters the stores; identity for part-ordered models). Skinned vertices leave through a small
+//     per-warp staging buffer as full-sector 8-byte stores (one vertex per lane would otherwise write 4-byte pieces at a
+//     12-byte stride);
 //   * statistics: each thread sums its vertex over the chunk's meshes while skinning; after the chunk the two mesh halves
 //     are combined, and a second pass re-reads the just-written vertices from L2 (not HBM) for the mean distance.
 // The 24 posed joints come from smpl_fk_kernel, the 21 picked + 45 regressed joints from a small gather kernel.
@@ -45,36 +52,38 @@ constexpr int NPMAX = 112;                  // meshes per chunk = MMA N (multipl
 constexpr int PTILE = GV * 128;             // posedirs tile [128 rows][64 k] fp16: 16,384 B
 constexpr int FTILE = NPMAX * 128;          // feature tile  [112 rows][64 k] fp16: 14,336 B
 constexpr int RING = 3;
-constexpr int ASUB = 16;                    // meshes per skinning-transform sub-chunk
-constexpr int AMESH = NJ * 12;              // floats per mesh: 24 joints x (3 rows x 4)
-constexpr int ASUB_BYTES = ASUB * AMESH * 4;   // 18,432
+constexpr int MS = 4;                       // meshes per skinning (T) sub-chunk
+constexpr int TN = MS * 12;                 // T-GEMM N: 48 columns = 4 meshes x (3 rows x 4)
+constexpr int ASUB = 8;                     // meshes per A^T buffer = two T sub-chunks
+constexpr int ATPART = TN * 32 * 2;         // one fp16 part of one T sub-chunk, K padded 24 -> 32: 3,072 B
+constexpr int ABUF_BYTES = 2 * 2 * ATPART;  // [tsub][hi|lo]: 12,288 B
+constexpr int ARING = 3;
+constexpr int WPART = GV * 32 * 2;          // one fp16 part of a group's skinning weights [128][32]: 8,192 B
+constexpr int WG_BYTES = 2 * WPART;         // 16,384 B
+constexpr int TCOL0 = 3 * NPMAX;            // TMEM column of the first T accumulator (336); the second follows at + TN
 constexpr int GPI = 6;                      // vertex groups per work item
 constexpr int NRANGE = NGRP / GPI;          // 9
 static_assert(NRANGE * GPI == NGRP, "vertex groups must split evenly into work items");
-constexpr int NQF = 12;                     // specialised bodies for 1..12 joints per warp tile
-constexpr int NQTAB = NJ;                   // table width (rolled fallback handles up to all 24 joints)
 constexpr int EPI_WARPS = 8;
-constexpr int STG_MESHES = 2;
 constexpr int THREADS = 384;
 
 struct FusedSmem {
   static constexpr int F_OFF = 0;                                              // [hi kb0..3 | lo kb0..3] feature tiles
   static constexpr int RING_OFF = F_OFF + 8 * FTILE;                           // 114,688
-  static constexpr int A_OFF = RING_OFF + RING * PTILE;                        // 163,840
-  static constexpr int STG_OFF = A_OFF + 2 * ASUB_BYTES;                       // 200,704
-  static constexpr int SUM_OFF = STG_OFF + EPI_WARPS * STG_MESHES * 384;       // 212,992
-  static constexpr int BAR_OFF = SUM_OFF + 2 * 2 * GV * 16;                    // sums [parity][half][128] float4: 221,184
+  static constexpr int AT_OFF = RING_OFF + RING * PTILE;                       // 163,840
+  static constexpr int W_OFF = AT_OFF + ARING * ABUF_BYTES;                    // 200,704
+  static constexpr int STG_OFF = W_OFF + WG_BYTES;                             // 217,088
+  static constexpr int SUM_OFF = STG_OFF + EPI_WARPS * 2 * 384;                // 223,232
+  static constexpr int BAR_OFF = SUM_OFF + 2 * GV * 16;                        // sums [half][128] float4: 227,328
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
 };
 static_assert(FusedSmem::RING_OFF % 1024 == 0 && FusedSmem::TOTAL <= 232448, "shared memory budget");
 
 struct FusedArgs {
-  int M, cs, n_chunks, stats;
+  int M, cs, n_chunks, stats, nsu;   // nsu = A^T buffers (8 meshes) per chunk
   float inv_scale;
-  const float* A;            // [M][288] skinning transforms (smpl_fk_kernel)
-  const int* tile_nq;        // [NWT]
-  const int* tile_joff;      // [NWT][24] float4 offset of the joint inside one mesh's A block (joint * 3)
-  const float* tile_w;       // [NWT][24][32]
+  const uint8_t* AT;         // [n_chunks][nsu][ABUF_BYTES] skinning transforms, fp16 hi/lo, UMMA core-matrix order (smpl_fk_kernel)
+  const uint8_t* Wg;         // [NGRP][WG_BYTES] skinning weights of each 128-vertex group, fp16 hi/lo, UMMA core-matrix order
   const float4* vt;          // [NGRP*128] (v_template xyz of the permuted vertex, original vertex index as int bits; -1 = padding)
   const int* tile_base;      // [NWT] original index of the tile's first vertex if its vertices are consecutive, else -1
   float* vertices;           // [M][6890][3]
@@ -82,23 +91,9 @@ struct FusedArgs {
   float* mean;               // [n_chunks][6890][3] or null
 };
 
-__device__ __forceinline__ void ffma2(float2& acc, float s, float x, float y) {
-  unsigned long long a, b, c, d;
-  asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(s));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(x), "f"(y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(acc.x), "f"(acc.y));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(d));
-}
-
 struct EpiCtx {
-  const FusedArgs* args;
-  uint32_t taddr;            // TMEM address of (this warp's lane quarter, column 0)
-  int lane, quarter, half, tile, chunk_base, cs;
-  const float4* a_smem;      // [2][ASUB][72] float4
-  float* stg;                // this warp's staging buffer [STG_MESHES][96]
-  uint64_t* a_full; uint64_t* a_empty;
-  int abuf; uint32_t aphase;
+  int lane, chunk_base;
+  float* stg;                // this warp's staging buffer [2][96]
 };
 
 // two staged meshes (m_first, m_first + 1; the second only if `two`) -> HBM
@@ -122,101 +117,8 @@ __device__ __forceinline__ void flush_pair(const EpiCtx& c, float* vertices, int
   __syncwarp();
 }
 
-__device__ __forceinline__ void tmem_ld_32x2(uint32_t taddr, uint32_t& r0, uint32_t& r1) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
-}
-
-// Pass 1 of one (chunk, 128-vertex group) for this warp: skin its 32 vertices for its half of every 16-mesh sub-chunk.
-// NQ > 0: exactly NQ joints, joint loop unrolled; NQ == 0: rolled loop over `nq` joints (tiles with more than NQF joints).
-// The mesh loop is ROLLED, two meshes per iteration, with the TMEM loads of the next pair in flight while the current pair
-// is skinned (a first version unrolled 8 meshes x 13 joint-count bodies and ptxas unrolled the sub-chunk loop on top:
-// 120k instructions, instruction-cache bound at 4.0 ms per 25,600 meshes).
-template <int NQ>
-__device__ __forceinline__ void fused_tile_pass1(EpiCtx& c, int nq, float& sx, float& sy, float& sz) {
-  const FusedArgs& a = *c.args;
-  const int lane = c.lane, t = c.tile;
-  const float inv_scale = a.inv_scale;
-  float* const vertices = a.vertices;
-  const int* const tjoff = a.tile_joff + t * NQTAB;
-  const float* const tw = a.tile_w + (size_t)t * NQTAB * 32 + lane;
-  constexpr int NW = NQ > 0 ? NQ : 1;
-  float w[NW]; int joff[NW];
-  if constexpr (NQ > 0) {
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) { w[q] = tw[q * 32]; joff[q] = tjoff[q]; }
-  }
-  const float4 vt = a.vt[t * 32 + lane];
-  const int orig = __float_as_int(vt.w);
-  const bool valid = orig >= 0;
-  const int tbase = a.tile_base[t];
-  const int tcnt = min(32, NV - t * 32);
-  const int nsc = (c.cs + ASUB - 1) / ASUB;
-  auto skin = [&](const float4* Ag, uint32_t xr, uint32_t yr, uint32_t zr, float& ox, float& oy, float& oz) {
-    float2 r[6];
-#pragma unroll
-    for (int e = 0; e < 6; ++e) r[e] = make_float2(0.f, 0.f);
-    if constexpr (NQ > 0) {
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const float4 r0 = Ag[joff[q]], r1 = Ag[joff[q] + 1], r2 = Ag[joff[q] + 2];
-        const float u = w[q];
-        ffma2(r[0], u, r0.x, r0.y); ffma2(r[1], u, r0.z, r0.w);
-        ffma2(r[2], u, r1.x, r1.y); ffma2(r[3], u, r1.z, r1.w);
-        ffma2(r[4], u, r2.x, r2.y); ffma2(r[5], u, r2.z, r2.w);
-      }
-    } else {
-#pragma unroll 1
-      for (int q = 0; q < nq; ++q) {
-        const int jo = tjoff[q];
-        const float u = tw[q * 32];
-        const float4 r0 = Ag[jo], r1 = Ag[jo + 1], r2 = Ag[jo + 2];
-        ffma2(r[0], u, r0.x, r0.y); ffma2(r[1], u, r0.z, r0.w);
-        ffma2(r[2], u, r1.x, r1.y); ffma2(r[3], u, r1.z, r1.w);
-        ffma2(r[4], u, r2.x, r2.y); ffma2(r[5], u, r2.z, r2.w);
-      }
-    }
-    const float x = fmaf(__uint_as_float(xr), inv_scale, vt.x);
-    const float y = fmaf(__uint_as_float(yr), inv_scale, vt.y);
-    const float z = fmaf(__uint_as_float(zr), inv_scale, vt.z);
-    ox = fmaf(r[1].x, z, fmaf(r[0].y, y, r[0].x * x)) + r[1].y;
-    oy = fmaf(r[3].x, z, fmaf(r[2].y, y, r[2].x * x)) + r[3].y;
-    oz = fmaf(r[5].x, z, fmaf(r[4].y, y, r[4].x * x)) + r[5].y;
-  };
-#pragma unroll 1
-  for (int sc = 0; sc < nsc; ++sc) {
-    mbar_wait(&c.a_full[c.abuf], c.aphase, 31);
-    const int m_lo = sc * ASUB + c.half * 8;
-    const int cnt = min(8, c.cs - m_lo);
-    if (cnt > 0) {
-      const float4* Ab = c.a_smem + (size_t)c.abuf * (ASUB * 72) + (size_t)(c.half * 8) * 72;
-      uint32_t x0, x1, y0, y1, z0, z1;
-      tmem_ld_32x2(c.taddr + (uint32_t)m_lo, x0, x1);
-      tmem_ld_32x2(c.taddr + (uint32_t)(NPMAX + m_lo), y0, y1);
-      tmem_ld_32x2(c.taddr + (uint32_t)(2 * NPMAX + m_lo), z0, z1);
-#pragma unroll 1
-      for (int mi = 0; mi < cnt; mi += 2) {
-        tmem_ld_wait();
-        const uint32_t cx0 = x0, cx1 = x1, cy0 = y0, cy1 = y1, cz0 = z0, cz1 = z1;
-        if (mi + 2 < cnt) {                      // next pair's accumulators in flight while this pair is skinned
-          tmem_ld_32x2(c.taddr + (uint32_t)(m_lo + mi + 2), x0, x1);
-          tmem_ld_32x2(c.taddr + (uint32_t)(NPMAX + m_lo + mi + 2), y0, y1);
-          tmem_ld_32x2(c.taddr + (uint32_t)(2 * NPMAX + m_lo + mi + 2), z0, z1);
-        }
-        const bool two = mi + 1 < cnt;
-        float ox0, oy0, oz0, ox1 = 0.f, oy1 = 0.f, oz1 = 0.f;
-        skin(Ab + mi * 72, cx0, cy0, cz0, ox0, oy0, oz0);
-        if (two) skin(Ab + (mi + 1) * 72, cx1, cy1, cz1, ox1, oy1, oz1);
-        sx += ox0 + ox1; sy += oy0 + oy1; sz += oz0 + oz1;
-        float* s = c.stg + 3 * lane;
-        s[0] = ox0; s[1] = oy0; s[2] = oz0;
-        s[96] = ox1; s[97] = oy1; s[98] = oz1;
-        flush_pair(c, vertices, m_lo + mi, two, tbase, tcnt, orig, valid);
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&c.a_empty[c.abuf]);
-    if (++c.abuf == 2) { c.abuf = 0; c.aphase ^= 1; }
-  }
+__device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -230,11 +132,15 @@ smpl_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_consta
   uint64_t* f_empty = f_full + 1;
   uint64_t* ring_full = f_empty + 1;        // [RING]
   uint64_t* ring_empty = ring_full + RING;  // [RING]
-  uint64_t* tmem_full = ring_empty + RING;
-  uint64_t* tmem_empty = tmem_full + 1;
-  uint64_t* a_full = tmem_empty + 1;        // [2]
-  uint64_t* a_empty = a_full + 2;           // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(a_empty + 2);
+  uint64_t* blend_full = ring_empty + RING;
+  uint64_t* blend_empty = blend_full + 1;
+  uint64_t* a_full = blend_empty + 1;       // [ARING]
+  uint64_t* a_empty = a_full + ARING;       // [ARING]
+  uint64_t* w_full = a_empty + ARING;
+  uint64_t* w_empty = w_full + 1;
+  uint64_t* t_full = w_empty + 1;           // [2]
+  uint64_t* t_empty = t_full + 2;           // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = args.n_chunks * NRANGE;
@@ -243,8 +149,10 @@ smpl_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_consta
   if (warp == 1 && lane == 0) {
     mbar_init(f_full, 1); mbar_init(f_empty, 1);
     for (int s = 0; s < RING; ++s) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
-    mbar_init(tmem_full, 1); mbar_init(tmem_empty, EPI_WARPS);
-    for (int b = 0; b < 2; ++b) { mbar_init(&a_full[b], 1); mbar_init(&a_empty[b], EPI_WARPS); }
+    mbar_init(blend_full, 1); mbar_init(blend_empty, EPI_WARPS);
+    for (int b = 0; b < ARING; ++b) { mbar_init(&a_full[b], 1); mbar_init(&a_empty[b], 1); }
+    mbar_init(w_full, 1); mbar_init(w_empty, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], EPI_WARPS / 2); }   // a T buffer belongs to one mesh half
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_base_slot);
@@ -278,17 +186,22 @@ smpl_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_consta
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    constexpr uint32_t idesc = umma_idesc_f16(NPMAX);
-    int stage = 0; uint32_t phase = 0, fphase = 0, tphase = 0;
+    // ===================================================== MMA issuer: blend GEMM of a group, then its skinning GEMMs
+    constexpr uint32_t idesc = umma_idesc_f16(NPMAX), idesc_t = umma_idesc_f16(TN);
+    int stage = 0; uint32_t phase = 0, fphase = 0, bphase = 0, wphase = 0;
+    int ab = 0; uint32_t aphase = 0;
+    int tb = 0; uint32_t tphase = 0;
     const uint32_t f_base = smem_u32(smem + L::F_OFF), r_base = smem_u32(smem + L::RING_OFF);
+    const uint32_t at_base = smem_u32(smem + L::AT_OFF), w_base = smem_u32(smem + L::W_OFF);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int chunk = item / NRANGE;
+      const int cs = min(args.cs, args.M - chunk * args.cs);
       mbar_wait(f_full, fphase, 43);
       fphase ^= 1;
       tc_fence_after_sync();
       for (int g = 0; g < GPI; ++g) {
-        mbar_wait(tmem_empty, tphase ^ 1, 44);          // the epilogue has read the previous group's accumulators
-        tphase ^= 1;
+        mbar_wait(blend_empty, bphase ^ 1, 44);          // the epilogue has read the previous group's v_posed accumulators
+        bphase ^= 1;
         tc_fence_after_sync();
         for (int plane = 0; plane < 3; ++plane) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(plane * NPMAX);
@@ -314,104 +227,177 @@ smpl_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_consta
             if (++stage == RING) { stage = 0; phase ^= 1; }
           }
         }
-        if (elect_one()) umma_commit(tmem_full);
+        if (elect_one()) umma_commit(blend_full);
+        // ---- skinning GEMMs: T[128 vertices][4 meshes x 12] = W_g [128][32] x A^T [48][32]^T per 4-mesh sub-chunk
+        mbar_wait(w_full, wphase, 48);
+        wphase ^= 1;
+        tc_fence_after_sync();
+        for (int s = 0; s < args.nsu; ++s) {
+          mbar_wait(&a_full[ab], aphase, 49);
+          tc_fence_after_sync();
+          for (int ts = 0; ts < 2; ++ts) {
+            if (s * ASUB + ts * MS >= cs) break;
+            mbar_wait(&t_empty[tb], tphase ^ 1, 50);
+            tc_fence_after_sync();
+            const uint32_t d_t = tmem_base + (uint32_t)(TCOL0 + tb * TN);
+            const uint32_t at = at_base + (uint32_t)(ab * ABUF_BYTES + ts * 2 * ATPART);
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {           // K = 32 joints (24 used): two K = 16 steps = core-matrix pairs
+                const uint64_t wh = umma_desc_nosw(w_base + ks * 2 * 2048, 2048, 128), wl = umma_desc_nosw(w_base + WPART + ks * 2 * 2048, 2048, 128);
+                const uint64_t ah = umma_desc_nosw(at + ks * 2 * 768, 768, 128), al = umma_desc_nosw(at + ATPART + ks * 2 * 768, 768, 128);
+                umma_f16(d_t, wh, ah, idesc_t, ks != 0 ? 1u : 0u);
+                umma_f16(d_t, wh, al, idesc_t, 1u);
+                umma_f16(d_t, wl, ah, idesc_t, 1u);
+              }
+            }
+            if (elect_one()) umma_commit(&t_full[tb]);
+            if (++tb == 2) { tb = 0; tphase ^= 1; }
+          }
+          if (elect_one()) umma_commit(&a_empty[ab]);
+          if (++ab == ARING) { ab = 0; aphase ^= 1; }
+        }
+        if (elect_one()) umma_commit(w_empty);
       }
       if (elect_one()) umma_commit(f_empty);            // the resident features may be replaced once every MMA of the item retired
     }
     __syncwarp();
   } else if (warp == 3) {
-    // ===================================================== skinning-transform loader: 16-mesh sub-chunks, 1-D bulk copies
-    int abuf = 0; uint32_t aphase = 0;
+    // ===================================================== loader of the skinning operands (1-D bulk copies): W per group,
+    // A^T per 8 meshes -- both already in UMMA core-matrix order in HBM
+    int ab = 0; uint32_t aphase = 0, wphase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int chunk = item / NRANGE;
-      const int m0 = chunk * args.cs, cs = min(args.cs, args.M - m0);
-      const int nsc = (cs + ASUB - 1) / ASUB;
-      for (int g = 0; g < GPI; ++g)
-        for (int sc = 0; sc < nsc; ++sc) {
-          mbar_wait(&a_empty[abuf], aphase ^ 1, 46);
-          const uint32_t bytes = (uint32_t)min(ASUB, cs - sc * ASUB) * AMESH * 4;
-          if (elect_one()) mbar_arrive_expect_tx(&a_full[abuf], bytes);
-          if (elect_one()) bulk_load_1d(smem + L::A_OFF + abuf * ASUB_BYTES, args.A + (size_t)(m0 + sc * ASUB) * AMESH, bytes, &a_full[abuf]);
-          if (++abuf == 2) { abuf = 0; aphase ^= 1; }
+      const int chunk = item / NRANGE, g0 = (item - chunk * NRANGE) * GPI;
+      for (int g = g0; g < g0 + GPI; ++g) {
+        mbar_wait(w_empty, wphase ^ 1, 51);
+        wphase ^= 1;
+        if (elect_one()) mbar_arrive_expect_tx(w_full, WG_BYTES);
+        if (elect_one()) bulk_load_1d(smem + L::W_OFF, args.Wg + (size_t)g * WG_BYTES, WG_BYTES, w_full);
+        for (int s = 0; s < args.nsu; ++s) {
+          mbar_wait(&a_empty[ab], aphase ^ 1, 46);
+          if (elect_one()) mbar_arrive_expect_tx(&a_full[ab], ABUF_BYTES);
+          if (elect_one()) bulk_load_1d(smem + L::AT_OFF + ab * ABUF_BYTES, args.AT + ((size_t)chunk * args.nsu + s) * ABUF_BYTES, ABUF_BYTES, &a_full[ab]);
+          if (++ab == ARING) { ab = 0; aphase ^= 1; }
         }
+      }
     }
     __syncwarp();
   } else if (warp >= 4) {
     // ===================================================== epilogue: 8 warps = 4 TMEM lane quarters x 2 mesh halves
     EpiCtx c;
-    c.args = &args; c.lane = lane; c.quarter = warp & 3; c.half = (warp - 4) >> 2;
-    c.taddr = tmem_base + ((uint32_t)(c.quarter * 32) << 16);
-    c.a_smem = reinterpret_cast<const float4*>(smem + L::A_OFF);
-    c.stg = reinterpret_cast<float*>(smem + L::STG_OFF) + (warp - 4) * STG_MESHES * 96;
-    c.a_full = a_full; c.a_empty = a_empty; c.abuf = 0; c.aphase = 0;
-    float4* sums = reinterpret_cast<float4*>(smem + L::SUM_OFF);          // [parity][half][128]
-    uint32_t tphase = 0;
-    int gcount = 0;
+    const int quarter = warp & 3, half = (warp - 4) >> 2;
+    c.lane = lane;
+    c.stg = reinterpret_cast<float*>(smem + L::STG_OFF) + (warp - 4) * 2 * 96;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    float4* sums = reinterpret_cast<float4*>(smem + L::SUM_OFF);          // [half][128]
+    const float inv_scale = args.inv_scale;
+    float* const vertices = args.vertices;
+    uint32_t bphase = 0, tphase = 0;
+    unsigned kcount = 0;                     // T sub-chunks issued so far: sub-chunk k (global count) lives in T buffer k & 1
 #pragma unroll 1
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int chunk = item / NRANGE, g0 = (item - chunk * NRANGE) * GPI;
       c.chunk_base = chunk * args.cs;
-      c.cs = min(args.cs, args.M - c.chunk_base);
+      const int cs = min(args.cs, args.M - c.chunk_base);
 #pragma unroll 1
-      for (int g = g0; g < g0 + GPI; ++g, ++gcount) {        // NOT unrolled: the body holds 13 specialised skinning loops
-        c.tile = g * 4 + c.quarter;
-        const int nq = args.tile_nq[c.tile];
-        mbar_wait(tmem_full, tphase, 47);
-        tphase ^= 1;
+      for (int g = g0; g < g0 + GPI; ++g) {
+        const int tile = g * 4 + quarter;
+        const float4 vt = args.vt[tile * 32 + lane];
+        const int orig = __float_as_int(vt.w);
+        const bool valid = orig >= 0;
+        const int tbase = args.tile_base[tile];
+        const int tcnt = min(32, NV - tile * 32);
+        mbar_wait(blend_full, bphase, 47);
+        bphase ^= 1;
         tc_fence_after_sync();
         float sx = 0.f, sy = 0.f, sz = 0.f;
-        switch (nq) {
-          case 1: fused_tile_pass1<1>(c, nq, sx, sy, sz); break;
-          case 2: fused_tile_pass1<2>(c, nq, sx, sy, sz); break;
-          case 3: fused_tile_pass1<3>(c, nq, sx, sy, sz); break;
-          case 4: fused_tile_pass1<4>(c, nq, sx, sy, sz); break;
-          case 5: fused_tile_pass1<5>(c, nq, sx, sy, sz); break;
-          case 6: fused_tile_pass1<6>(c, nq, sx, sy, sz); break;
-          case 7: fused_tile_pass1<7>(c, nq, sx, sy, sz); break;
-          case 8: fused_tile_pass1<8>(c, nq, sx, sy, sz); break;
-          case 9: fused_tile_pass1<9>(c, nq, sx, sy, sz); break;
-          case 10: fused_tile_pass1<10>(c, nq, sx, sy, sz); break;
-          case 11: fused_tile_pass1<11>(c, nq, sx, sy, sz); break;
-          case 12: fused_tile_pass1<12>(c, nq, sx, sy, sz); break;
-          default: fused_tile_pass1<0>(c, nq, sx, sy, sz); break;
+        const int nT = (cs + MS - 1) / MS;
+        const int k0 = (int)((kcount ^ (unsigned)half) & 1u);   // this half takes the sub-chunks that land in T buffer `half`
+#pragma unroll 1
+        for (int k = k0; k < nT; k += 2) {               // one T sub-chunk = 4 meshes, both pairs skinned by this warp
+          mbar_wait(&t_full[half], tphase, 52);
+          tphase ^= 1;
+          tc_fence_after_sync();
+          const int m0 = k * MS;
+          const int cnt = min(MS, cs - m0);
+          uint32_t t[48], vx[4], vy[4], vz[4];
+          const uint32_t tcol = taddr + (uint32_t)(TCOL0 + half * TN);
+#pragma unroll
+          for (int q = 0; q < 6; ++q) tmem_ld_32x8(tcol + q * 8, *reinterpret_cast<uint32_t(*)[8]>(&t[q * 8]));
+          tmem_ld_32x4(taddr + (uint32_t)m0, vx);
+          tmem_ld_32x4(taddr + (uint32_t)(NPMAX + m0), vy);
+          tmem_ld_32x4(taddr + (uint32_t)(2 * NPMAX + m0), vz);
+          tmem_ld_wait();
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[half]);    // T is in registers: the MMAs of this half's next sub-chunk may start
+#pragma unroll
+          for (int pr = 0; pr < 2; ++pr) {
+            if (2 * pr < cnt) {
+              const bool two = 2 * pr + 1 < cnt;
+              float o[6];
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const int mm = 2 * pr + j;
+                const float x = fmaf(__uint_as_float(vx[mm]), inv_scale, vt.x);
+                const float y = fmaf(__uint_as_float(vy[mm]), inv_scale, vt.y);
+                const float z = fmaf(__uint_as_float(vz[mm]), inv_scale, vt.z);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                  const float* T = reinterpret_cast<const float*>(&t[mm * 12 + i * 4]);
+                  o[j * 3 + i] = fmaf(T[2], z, fmaf(T[1], y, T[0] * x)) + T[3];
+                }
+              }
+              if (!two) { o[3] = 0.f; o[4] = 0.f; o[5] = 0.f; }
+              sx += o[0] + o[3]; sy += o[1] + o[4]; sz += o[2] + o[5];
+              float* s = c.stg + 3 * lane;
+              s[0] = o[0]; s[1] = o[1]; s[2] = o[2];
+              s[96] = o[3]; s[97] = o[4]; s[98] = o[5];
+              flush_pair(c, vertices, m0 + 2 * pr, two, tbase, tcnt, orig, valid);
+            }
+          }
         }
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty);          // accumulators free: the next group's MMAs overlap the statistics
+        if (lane == 0) mbar_arrive(blend_empty);         // v_posed accumulators free: the next group's MMAs overlap the statistics
         if (args.stats) {
-          const float4 vt = args.vt[c.tile * 32 + lane];
-          const int orig = __float_as_int(vt.w);
-          const bool valid = orig >= 0;
-          float4* mine = sums + ((gcount & 1) * 2 + c.half) * GV + c.quarter * 32 + lane;
-          float4* other = sums + ((gcount & 1) * 2 + (c.half ^ 1)) * GV + c.quarter * 32 + lane;
+          float4* mine = sums + half * GV + quarter * 32 + lane;
+          float4* other = sums + (half ^ 1) * GV + quarter * 32 + lane;
           *mine = make_float4(sx, sy, sz, 0.f);
           asm volatile("bar.sync 1, 256;" ::: "memory");
           const float4 o = *other;
-          const float inv_n = 1.0f / (float)c.cs;
+          const float inv_n = 1.0f / (float)cs;
           const float mx = (sx + o.x) * inv_n, my = (sy + o.y) * inv_n, mz = (sz + o.z) * inv_n;
           // pass 2: mean distance to the mean over this warp's meshes, re-read from L2 (written by this warp a moment ago)
           float dsum = 0.f;
           if (valid) {
-            const int nsc = (c.cs + ASUB - 1) / ASUB;
-            for (int sc = 0; sc < nsc; ++sc) {
-              const int m_lo = sc * ASUB + c.half * 8;
-              const int cnt = min(8, c.cs - m_lo);
-#pragma unroll 4
-              for (int mi = 0; mi < cnt; ++mi) {
-                const float* v = args.vertices + (size_t)(c.chunk_base + m_lo + mi) * NV3 + 3 * orig;
-                const float dx = __ldcg(v) - mx, dy = __ldcg(v + 1) - my, dz = __ldcg(v + 2) - mz;
-                dsum += sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+#pragma unroll 1
+            for (int k = k0; k < nT; k += 4) {           // two of this warp's sub-chunks = 8 meshes per iteration: 24 loads in flight
+              float px[8], py[8], pz[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int m = (k + 2 * (u >> 2)) * MS + (u & 3);
+                const float* v = vertices + (size_t)(c.chunk_base + min(m, cs - 1)) * NV3 + 3 * orig;
+                px[u] = __ldcg(v); py[u] = __ldcg(v + 1); pz[u] = __ldcg(v + 2);
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                const int m = (k + 2 * (u >> 2)) * MS + (u & 3);
+                const float dx = px[u] - mx, dy = py[u] - my, dz = pz[u] - mz;
+                if (m < cs) dsum += sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
               }
             }
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");     // everyone has read the position sums
           mine->w = dsum;
           asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (c.half == 0 && valid) {
+          if (half == 0 && valid) {
             args.unc[(size_t)chunk * NV + orig] = (dsum + other->w) * inv_n;
             if (args.mean) { float* mo = args.mean + ((size_t)chunk * NV + orig) * 3; mo[0] = mx; mo[1] = my; mo[2] = mz; }
           }
+          asm volatile("bar.sync 1, 256;" ::: "memory");     // the sums buffer may be rewritten by the next group
         }
+        kcount += (unsigned)nT;
       }
     }
   }
@@ -432,11 +418,15 @@ __device__ __forceinline__ void mat3_mul(const float* a, const float* b, float* 
 }
 
 // warp = mesh, lane = joint: J = J_template + J_shapedirs beta (the regressor folded at create time), the 24-joint chain
-// walked level by level through shared memory, A_j = [R_j | t_j - R_j J_j] (smplx batch_rigid_transform).
+// walked level by level through shared memory, A_j = [R_j | t_j - R_j J_j] (smplx batch_rigid_transform). The 12 entries of
+// A_j are written as fp16 hi/lo pairs straight into the B operand of the skinning GEMM: chunk-major buffers of 8 meshes,
+// [T sub-chunk (4 meshes)][hi|lo][k-group (8 joints)][row group][8 rows][8 joints], row = mesh_in_sub-chunk * 12 + entry
+// (UMMA no-swizzle K-major core matrices: 128 contiguous bytes = 8 rows x 8 joints). The buffer is zeroed beforehand
+// (joints 24..31 and the meshes past the end of a chunk stay zero).
 __global__ void __launch_bounds__(256) smpl_fk_kernel(const float* __restrict__ betas, int Mb, const float* __restrict__ global_orient,
                                                       int Mg, const float* __restrict__ body_pose, int M,
                                                       const float* __restrict__ J_template, const float* __restrict__ J_shapedirs,
-                                                      FkTree tree, float* __restrict__ A, float* __restrict__ joints) {
+                                                      FkTree tree, int cs, int nsu, uint8_t* __restrict__ AT, float* __restrict__ joints) {
   __shared__ float sG[8][NJ][12];
   const int warp = threadIdx.x >> 5, j = threadIdx.x & 31;
   const int m = blockIdx.x * 8 + warp;
@@ -485,11 +475,22 @@ __global__ void __launch_bounds__(256) smpl_fk_kernel(const float* __restrict__ 
     __syncwarp();
   }
   if (j < NJ) {
-    float4* Am = reinterpret_cast<float4*>(A + (size_t)m * AMESH) + j * 3;
+    const int chunk = m / cs, ml = m - chunk * cs;
+    const int su = ml / ASUB, ts = (ml % ASUB) / MS, mm = ml % MS;
+    uint8_t* buf = AT + ((size_t)chunk * nsu + su) * ABUF_BYTES + (size_t)ts * 2 * ATPART;
+    const int koff = (j >> 3) * 768 + (j & 7) * 2;                 // k-group stride 6 row groups x 128 B; 2 B per joint
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const float t = G[9 + i] - fmaf(G[i * 3 + 2], Jj[2], fmaf(G[i * 3 + 1], Jj[1], G[i * 3] * Jj[0]));
-      Am[i] = make_float4(G[i * 3], G[i * 3 + 1], G[i * 3 + 2], t);
+      const float a4[4] = {G[i * 3], G[i * 3 + 1], G[i * 3 + 2], t};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = mm * 12 + i * 4 + e;
+        const int off = koff + (r >> 3) * 128 + (r & 7) * 16;
+        const __half h = __float2half_rn(a4[e]);
+        *reinterpret_cast<__half*>(buf + off) = h;
+        *reinterpret_cast<__half*>(buf + ATPART + off) = __float2half_rn(a4[e] - __half2float(h));
+      }
     }
     if (joints) {
       float* jo = joints + ((size_t)m * NOUTJ + j) * 3;
@@ -546,7 +547,8 @@ struct SmplFused {
   __half *p_hi = nullptr, *p_lo = nullptr;     // [PROWS][KP] posedirs/shapedirs planes (scaled by 2^ex)
   CUtensorMap tmPhi, tmPlo;
   float inv_scale = 1.f;
-  int* tile_nq = nullptr; int* tile_joff = nullptr; float* tile_w = nullptr; float4* vt = nullptr; int* tile_base = nullptr;
+  uint8_t* Wg = nullptr;                        // [NGRP][WG_BYTES] skinning weights, fp16 hi/lo, UMMA core-matrix order
+  float4* vt = nullptr; int* tile_base = nullptr;
   float *J_template = nullptr, *J_shapedirs = nullptr;
   int *pick_ids = nullptr, *reg_rowptr = nullptr, *reg_col = nullptr;
   float* reg_val = nullptr;
@@ -562,7 +564,7 @@ namespace hp3d {
 void smpl_fused_destroy(void* p) {
   if (!p) return;
   SmplFused* h = (SmplFused*)p;
-  cudaFree(h->p_hi); cudaFree(h->p_lo); cudaFree(h->tile_nq); cudaFree(h->tile_joff); cudaFree(h->tile_w); cudaFree(h->vt);
+  cudaFree(h->p_hi); cudaFree(h->p_lo); cudaFree(h->Wg); cudaFree(h->vt);
   cudaFree(h->tile_base); cudaFree(h->J_template); cudaFree(h->J_shapedirs); cudaFree(h->pick_ids); cudaFree(h->reg_rowptr);
   cudaFree(h->reg_col); cudaFree(h->reg_val);
   delete h;
@@ -592,30 +594,28 @@ int smpl_fused_create(const hp3d_smpl_model* md, const float* Jt, const float* J
   for (int j = 0; j < NJ; ++j) { h->tree.parent[j] = (int8_t)md->parents[j]; h->tree.depth[j] = (j == 0) ? 0 : (int8_t)(h->tree.depth[md->parents[j]] + 1); }
   h->tree.max_depth = 0;
   for (int j = 0; j < NJ; ++j) h->tree.max_depth = std::max<int>(h->tree.max_depth, h->tree.depth[j]);
-  // ---- vertex order: identity, unless clustering by dominant joint shortens the per-tile joint lists markedly (an
-  //      arbitrary weight layout then still gets short lists; runs of consecutive indices survive the stable sort)
+  // ---- vertex order. Skinning is a dense K = 24 contraction on the tensor cores, so its cost does NOT depend on which
+  //      joints the vertices of a tile use: ANY weight layout (part-ordered or not) runs at the same speed in the identity
+  //      order, which also keeps every warp's stores consecutive. HP3D_SMPL_ORDER=sorted forces a re-ordering by dominant
+  //      joint (tests of the scattered-store path); the per-tile joint counts are reported for information only.
   std::vector<int> order(NV);
   std::iota(order.begin(), order.end(), 0);
-  int sum_id, mx_id;
-  tile_joint_counts(md->lbs_weights, order, sum_id, mx_id);
+  tile_joint_counts(md->lbs_weights, order, h->nq_sum, h->nq_max);
   {
-    std::vector<int> dom(NV, 0), sorted = order;
-    for (int v = 0; v < NV; ++v) {
-      double best = -1.0;
-      for (int j = 0; j < NJ; ++j) if (md->lbs_weights[(size_t)v * NJ + j] > best) { best = md->lbs_weights[(size_t)v * NJ + j]; dom[v] = j; }
+    const char* e = getenv("HP3D_SMPL_ORDER");
+    if (e && !strcmp(e, "sorted")) {
+      std::vector<int> dom(NV, 0);
+      for (int v = 0; v < NV; ++v) {
+        double best = -1.0;
+        for (int j = 0; j < NJ; ++j) if (md->lbs_weights[(size_t)v * NJ + j] > best) { best = md->lbs_weights[(size_t)v * NJ + j]; dom[v] = j; }
+      }
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return dom[a] < dom[b]; });
+      h->permuted = 1;
+      tile_joint_counts(md->lbs_weights, order, h->nq_sum, h->nq_max);
     }
-    std::stable_sort(sorted.begin(), sorted.end(), [&](int a, int b) { return dom[a] < dom[b]; });
-    int sum_s, mx_s;
-    tile_joint_counts(md->lbs_weights, sorted, sum_s, mx_s);
-    const char* e = getenv("HP3D_SMPL_ORDER");     // "identity" / "sorted" force the choice (tests, experiments)
-    const bool force_sorted = e && !strcmp(e, "sorted"), force_id = e && !strcmp(e, "identity");
-    if (!force_id && (force_sorted || sum_s * 100 < sum_id * 85 || (mx_id > NQF && mx_s < mx_id))) {
-      order = sorted; h->permuted = 1; h->nq_sum = sum_s; h->nq_max = mx_s;
-    } else { h->nq_sum = sum_id; h->nq_max = mx_id; }
   }
-  // ---- tile tables
-  std::vector<int> tnq(NWT, 0), tjoff((size_t)NWT * NQTAB, 0), tbase(NWT, -1);
-  std::vector<float> tw((size_t)NWT * NQTAB * 32, 0.f);
+  // ---- per-vertex constants and per-tile store layout
+  std::vector<int> tbase(NWT, -1);
   std::vector<float4> vt((size_t)NGRP * GV);
   for (int p = 0; p < NGRP * GV; ++p) {
     if (p < NV) {
@@ -626,22 +626,26 @@ int smpl_fused_create(const hp3d_smpl_model* md, const float* Jt, const float* J
   }
   for (int t = 0; t < NWT; ++t) {
     const int p0 = t * 32, p1 = std::min(NV, p0 + 32);
-    int slot[NJ];
-    for (int j = 0; j < NJ; ++j) slot[j] = -1;
-    for (int p = p0; p < p1; ++p)
-      for (int j = 0; j < NJ; ++j) if (md->lbs_weights[(size_t)order[p] * NJ + j] != 0.0) slot[j] = 0;
-    int q = 0;
-    for (int j = 0; j < NJ; ++j) if (slot[j] == 0) { slot[j] = q; tjoff[(size_t)t * NQTAB + q] = j * 3; ++q; }
-    tnq[t] = std::max(q, 1);                 // a tile of all-zero weights still runs the 1-joint body with zero weights
-    for (int p = p0; p < p1; ++p)
-      for (int j = 0; j < NJ; ++j) {
-        const double w = md->lbs_weights[(size_t)order[p] * NJ + j];
-        if (w != 0.0) tw[((size_t)t * NQTAB + slot[j]) * 32 + (p - p0)] = (float)w;
-      }
     bool contig = p1 > p0;
     for (int p = p0 + 1; p < p1; ++p) contig &= (order[p] == order[p0] + (p - p0));
     tbase[t] = contig ? order[p0] : -1;
   }
+  // ---- skinning weights of every 128-vertex group as the A operand of the T-GEMM: [group][hi|lo][k-group (8 joints)]
+  //      [row group (8 vertices)][8 vertices][8 joints] fp16 (no-swizzle K-major core matrices), K padded 24 -> 32
+  std::vector<__half> wg((size_t)NGRP * WG_BYTES / 2, __float2half_rn(0.f));
+  for (int g = 0; g < NGRP; ++g)
+    for (int i = 0; i < GV; ++i) {
+      const int p = g * GV + i;
+      if (p >= NV) continue;
+      for (int j = 0; j < NJ; ++j) {
+        const double w = md->lbs_weights[(size_t)order[p] * NJ + j];
+        if (w == 0.0) continue;
+        const size_t off = (size_t)g * (WG_BYTES / 2) + (size_t)(j >> 3) * 1024 + (size_t)(i >> 3) * 64 + (size_t)(i & 7) * 8 + (j & 7);   // in halfs
+        const __half hv = __float2half_rn((float)w);
+        wg[off] = hv;
+        wg[off + WPART / 2] = __float2half_rn((float)(w - (double)__half2float(hv)));
+      }
+    }
   // ---- P' planes: row (g*3 + plane)*128 + i <-> coordinate `plane` of vertex order[g*128 + i]; power-of-two pre-scale
   double mx = 0.0;
   for (size_t i = 0; i < (size_t)NPF * NV3; ++i) mx = std::max(mx, fabs(md->posedirs[i]));
@@ -679,9 +683,7 @@ int smpl_fused_create(const hp3d_smpl_model* md, const float* Jt, const float* J
   std::vector<int> picks(md->extra_vertex_ids, md->extra_vertex_ids + NPICK);
   int rc = upload(&h->p_hi, ph.data(), ph.size());
   rc = rc ? rc : upload(&h->p_lo, pl.data(), pl.size());
-  rc = rc ? rc : upload(&h->tile_nq, tnq.data(), tnq.size());
-  rc = rc ? rc : upload(&h->tile_joff, tjoff.data(), tjoff.size());
-  rc = rc ? rc : upload(&h->tile_w, tw.data(), tw.size());
+  rc = rc ? rc : upload((__half**)&h->Wg, wg.data(), wg.size());
   rc = rc ? rc : upload(&h->vt, vt.data(), vt.size());
   rc = rc ? rc : upload(&h->tile_base, tbase.data(), tbase.size());
   rc = rc ? rc : upload(&h->J_template, Jt, (size_t)NJ * 3);
@@ -701,7 +703,11 @@ int smpl_fused_create(const hp3d_smpl_model* md, const float* Jt, const float* J
 }
 
 static size_t fused_feat_bytes(int M) { return align_up((size_t)M * KP * sizeof(__half), 1024); }
-size_t smpl_fused_workspace_bytes(int M) { return 2 * fused_feat_bytes(M) + align_up((size_t)M * AMESH * 4, 1024); }
+// A^T buffers: chunks of cs meshes in units of 8 -> at most M/8 + (number of chunks) units; chunks are >= 8 meshes in the
+// statistics mode (smaller sample counts take the chunk-of-112 path + the separate statistics kernel)
+static size_t fused_at_bytes(int M) { return align_up(((size_t)M / 8 + (size_t)M / 8 + 2) * ABUF_BYTES, 1024); }
+size_t smpl_fused_workspace_bytes(int M) { return 2 * fused_feat_bytes(M) + fused_at_bytes(M); }
+int smpl_fused_min_samples() { return 8; }
 
 void smpl_fused_info(const void* p, int* permuted, int* nq_sum, int* nq_max) {
   const SmplFused* h = (const SmplFused*)p;
@@ -710,7 +716,7 @@ void smpl_fused_info(const void* p, int* permuted, int* nq_sum, int* nq_max) {
   if (nq_max) *nq_max = h ? h->nq_max : 0;
 }
 
-// samples_per_image: N in [1, 112] with M % N == 0 -> chunk = image, `unc` [M/N][6890] (and optionally `mean` [M/N][6890][3])
+// samples_per_image: N in [8, 112] with M % N == 0 -> chunk = image, `unc` [M/N][6890] (and optionally `mean` [M/N][6890][3])
 // are written; 0 -> chunks of 112 consecutive meshes, no statistics.
 int smpl_fused_forward(void* p, const float* betas, int Mb, const float* global_orient, int Mg, const float* body_pose, int M,
                        int samples_per_image, float* vertices, float* joints, float* unc, float* mean, void* workspace,
@@ -719,11 +725,21 @@ int smpl_fused_forward(void* p, const float* betas, int Mb, const float* global_
   char* ws = (char*)workspace;
   __half* f_hi = (__half*)ws; ws += fused_feat_bytes(M);
   __half* f_lo = (__half*)ws; ws += fused_feat_bytes(M);
-  float* A = (float*)ws;
+  uint8_t* AT = (uint8_t*)ws;
+  FusedArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = M;
+  a.stats = (samples_per_image > 0 && unc) ? 1 : 0;
+  a.cs = samples_per_image > 0 ? samples_per_image : std::min(M, NPMAX);
+  a.n_chunks = cdiv(M, a.cs);
+  a.nsu = cdiv(a.cs, ASUB);
+  if ((size_t)a.n_chunks * a.nsu * ABUF_BYTES > fused_at_bytes(M)) { set_error("smpl_fused_forward: chunk size %d too small for the workspace", a.cs); return -1; }
   fused_feature_split_kernel<<<(unsigned)(((size_t)M * KP + 255) / 256), 256, 0, stream>>>(body_pose, betas, M / Mb, M, f_hi, f_lo);
   int rc = launch_status("fused_feature_split_kernel");
   if (rc) return rc;
-  smpl_fk_kernel<<<cdiv(M, 8), 256, 0, stream>>>(betas, Mb, global_orient, Mg, body_pose, M, h->J_template, h->J_shapedirs, h->tree, A, joints);
+  HP3D_CUDA(cudaMemsetAsync(AT, 0, (size_t)a.n_chunks * a.nsu * ABUF_BYTES, stream));
+  smpl_fk_kernel<<<cdiv(M, 8), 256, 0, stream>>>(betas, Mb, global_orient, Mg, body_pose, M, h->J_template, h->J_shapedirs, h->tree, a.cs, a.nsu,
+                                                  AT, joints);
   rc = launch_status("smpl_fk_kernel");
   if (rc) return rc;
   CUtensorMap tmFhi, tmFlo;
@@ -733,14 +749,8 @@ int smpl_fused_forward(void* p, const float* betas, int Mb, const float* global_
   rc = make_tmap_f16(&tmFhi, f_hi, 2, dims, st, box);
   rc = rc ? rc : make_tmap_f16(&tmFlo, f_lo, 2, dims, st, box);
   if (rc) return rc;
-  FusedArgs a;
-  memset(&a, 0, sizeof(a));
-  a.M = M;
-  a.stats = (samples_per_image > 0 && unc) ? 1 : 0;
-  a.cs = samples_per_image > 0 ? samples_per_image : std::min(M, NPMAX);
-  a.n_chunks = cdiv(M, a.cs);
   a.inv_scale = h->inv_scale;
-  a.A = A; a.tile_nq = h->tile_nq; a.tile_joff = h->tile_joff; a.tile_w = h->tile_w; a.vt = h->vt; a.tile_base = h->tile_base;
+  a.AT = AT; a.Wg = h->Wg; a.vt = h->vt; a.tile_base = h->tile_base;
   a.vertices = vertices; a.unc = a.stats ? unc : nullptr; a.mean = a.stats ? mean : nullptr;
   const int grid = std::min(a.n_chunks * NRANGE, h->num_sms);
   HP3D_SMEM_OPT_IN(smpl_fused_kernel, FusedSmem::TOTAL);

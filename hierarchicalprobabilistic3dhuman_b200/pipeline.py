@@ -51,9 +51,9 @@ class HotPathPipeline:
         self._stage = None
         self._slot = 0
         # libhp3d kernels launched by one pass, counted on the ncu launch list (profiles/): encoder 24 (input cast, arg-max
-        # decode, stem, max-pool, 19 convolutions, avg-pool), head 6, rot6d 1, mode SMPL 4 (shape blend, feature split, blend
-        # GEMM, LBS), sampler 1, per vertex chunk SMPL 4 + statistics 1, sample ranking 1
-        self.launches_per_pass = 24 + 6 + 1 + 4 + 1 + (4 + 1) * len(self.vertex_chunks) + 1
+        # decode, stem, max-pool, 19 convolutions, avg-pool), head 6, rot6d 1, mode SMPL 4 (feature split, FK, fused kernel,
+        # extra joints; + 1 memset node), sampler 1, per vertex chunk SMPL + statistics 4, sample ranking 1
+        self.launches_per_pass = 24 + 6 + 1 + 4 + 1 + 4 * len(self.vertex_chunks) + 1
 
     # ------------------------------------------------------------------ device-resident pass
     def _after_encoder(self, feats, proxy_rep=None, joints2d=None, joints2d_px=None):
@@ -72,16 +72,17 @@ class HotPathPipeline:
         for c, vch in enumerate(self.vertex_chunks):       # images [c*cb, (c+1)*cb): SMPL on cb*N meshes + statistics
             i0 = c * cb
             with _lib.nvtx("hp3d.smpl_samples+statistics"):
-                # SMPL on the chunk's cb*N meshes AND the per-vertex statistics of its cb images in one call (staged kernels by
-                # default; HP3D_SMPL=fused: one tensor-core kernel, the sample vertices are never re-read from HBM)
+                # SMPL on the chunk's cb*N meshes AND the per-vertex statistics of its cb images in one call: with the default
+                # fused kernel (8 <= N <= 112) v_posed never exists and the sample vertices are never re-read from HBM
                 _lib.check(L.hp3d_smpl_forward_stats(self.h_smpl, loc[i0:].data_ptr(), cb, glob_R[i0:].data_ptr(), cb, R[i0:].data_ptr(),
                                                      cb * N, N, vch.data_ptr(), self.joints[i0 * N:].data_ptr(),
                                                      self.uncertainty[i0:].data_ptr(), None, self.ws.data_ptr(), self.ws.numel(),
                                                      _lib.stream_ptr()), "hp3d_smpl_forward_stats")
             if self.on_vertices_chunk is not None:
                 self.on_vertices_chunk(c)
+        vertices = self.vertices if self.vertices is not None else (self.vertex_chunks[0] if C == 1 else None)
         res = dict(mode_vertices=out_mode.vertices, mode_joints=out_mode.joints, joints=self.joints, rotmats=R,
-                   uncertainty=self.uncertainty, vertices=self.vertices, betas=self.betas, pose_S=S, cam=cam)
+                   uncertainty=self.uncertainty, vertices=vertices, betas=self.betas, pose_S=S, cam=cam)
         if proxy_rep is not None or joints2d is not None or joints2d_px is not None:
             # rank the N samples of every image by 2D-joint consistency (sampling_utils.py:195-233)
             from .sampling import rank_samples_by_joints2d
@@ -136,7 +137,7 @@ class HotPathPipeline:
         assert x_host.is_pinned() and x_host.shape[0] == self.B
         st = self._staging(x_host)
         if return_vertices:
-            assert self.vertices is not None, "return_vertices needs a single (B,N,6890,3) vertices buffer"
+            assert self.vertices is not None or len(self.vertex_chunks) == 1, "return_vertices needs a single (B,N,6890,3) vertices buffer"
             for o in st["out"]:
                 if "vertices" not in o:
                     o["vertices"] = torch.empty(self.B, self.N, 6890, 3, dtype=torch.float32).pin_memory()

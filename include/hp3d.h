@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HP3D_VERSION 100
+#define HP3D_VERSION 200
 #define HP3D_NUM_VERTS 6890
 #define HP3D_NUM_JOINTS 24          /* SMPL skeleton incl. root */
 #define HP3D_NUM_BODY_JOINTS 23
@@ -63,18 +63,19 @@ int hp3d_smpl_forward(const hp3d_smpl* h, const float* betas, int Mb, const floa
                       void* workspace, size_t workspace_bytes, void* stream);
 /* hp3d_smpl_forward for B images x N samples (M = B * samples_per_image, image-major) that ALSO returns the per-vertex
  * statistics of utils/sampling_utils.py:189-190 per image: avg_dist [B*6890] = mean over the image's samples of the
- * distance to the image's mean mesh, mean_vertices [B*6890*3] (may be NULL). Default: hp3d_smpl_forward followed by
- * hp3d_vertex_uncertainty. With HP3D_SMPL=fused and samples_per_image <= 112 the statistics come out of the fused SMPL
- * kernel itself (csrc/smpl_fused.cu; parity-green, measured slower than the staged kernels -- DESIGN.md 5). */
+ * distance to the image's mean mesh, mean_vertices [B*6890*3] (may be NULL). With the default fused kernel
+ * (csrc/smpl_fused.cu) and 8 <= samples_per_image <= 112 the statistics come out of the SMPL kernel itself (the sample
+ * vertices are re-read from L2, never from HBM); otherwise (HP3D_SMPL=staged, other sample counts) it is hp3d_smpl_forward
+ * followed by hp3d_vertex_uncertainty. */
 int hp3d_smpl_forward_stats(const hp3d_smpl* h, const float* betas, int Mb, const float* global_orient, int Mg,
                             const float* body_pose, int M, int samples_per_image, float* vertices, float* joints,
                             float* avg_dist, float* mean_vertices, void* workspace, size_t workspace_bytes, void* stream);
-/* which path a handle takes (fused = 1 only with HP3D_SMPL=fused), whether the fused plan's vertices were
+/* which path a handle takes (fused = 1 unless HP3D_SMPL=staged or no tensor-map support), whether the fused plan's vertices were
  * re-ordered by dominant joint at create time, and the sum / maximum over the 216 32-vertex tiles of distinct skinning
  * joints (the fused kernel's skinning cost is proportional to the sum). */
 int hp3d_smpl_layout_info(const hp3d_smpl* h, int* fused, int* permuted, int* tile_joint_sum, int* tile_joint_max);
-/* stage-level entry points (used by tests / profiling; the default hp3d_smpl_forward = these three in order;
- * HP3D_SMPL=fused replaces them by ONE tensor-core kernel, csrc/smpl_fused.cu) */
+/* stage-level entry points of the STAGED path (HP3D_SMPL=staged: hp3d_smpl_forward = these three in order; used by tests /
+ * profiling). The default hp3d_smpl_forward is ONE tensor-core kernel (csrc/smpl_fused.cu): v_posed never exists in memory. */
 int hp3d_smpl_shape_blend(const hp3d_smpl* h, const float* betas, int Mb, float* v_shaped /*[Mb*20672]*/,
                           float* J /*[Mb*24*3]*/, void* stream);
 size_t hp3d_smpl_pose_blend_workspace_bytes(int M);   /* fp16 hi/lo pose features for the tensor-core blend */

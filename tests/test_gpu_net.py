@@ -121,7 +121,8 @@ def test_hot_path_pipeline_device_and_host_paths(built_lib):
     assert torch.equal(res["mode_vertices"], ref_mode.vertices)
     assert res["vertices"].shape == (B, N, 6890, 3) and torch.isfinite(res["vertices"]).all()
     mean, d = hp.vertex_uncertainty(res["vertices"])
-    assert torch.equal(d, res["uncertainty"])
+    # the fused SMPL kernel accumulates the statistics in its own order (per mesh half, then combined): same values to fp32 rounding
+    assert rel_err(d, res["uncertainty"]) < 1e-5
     xh = x.pin_memory()
     outs = []
     for _ in range(3):                                   # back-to-back calls exercise the double buffering

@@ -43,12 +43,6 @@ def test_exhausted_proposals_are_reported(built_lib):
     assert torch.isfinite(R).all()
 
 
-def _expected_rotation(S):
-    """E[R] = U diag(d log c / d s) V^T; the derivative by numerical integration of the MF normaliser
-    in quaternion form on a fine grid is overkill here -- use a large oracle Monte-Carlo run instead."""
-    raise NotImplementedError
-
-
 def test_philox_mode_statistics_match_oracle(built_lib):
     import hierarchicalprobabilistic3dhuman_b200 as hp
     # one image, all joints share diagonal U=V=I with different concentrations

@@ -15,7 +15,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert not missing, missing
     from hierarchicalprobabilistic3dhuman_b200 import _lib
     assert sorted(_lib.EXPORTS) == declared
-    assert _lib.lib().hp3d_version() == 100
+    assert _lib.lib().hp3d_version() == 200
 
 
 def test_argument_errors_do_not_need_a_gpu(built_lib):
