@@ -114,6 +114,20 @@ __device__ __forceinline__ void conv_epilogue_tile(uint32_t taddr, const float* 
   }
 }
 
+// SPLIT epilogue, part 0: pull this thread's residual record (hi and lo halves, BN fp16 each) into L2 at the START of the tile.
+// The residual is read after the last chunk has been summed; measured (profiles/r02t_ncu_full_summary.csv) the convolutions
+// with a skip connection ran 50 % (layer 1) / 20 % (layers 2-3) slower than their twins without one -- the block input had
+// long left L2 and the epilogue's tail sat on HBM latency while the MMA warp ran out of free TMEM chunks.
+template <int BN>
+__device__ __forceinline__ void split_prefetch_residual(const __half* __restrict__ residual, size_t off, int cout, bool store) {
+  if (!residual || !store) return;
+#pragma unroll
+  for (int b = 0; b < BN * 2; b += 128) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(residual + off) + b));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(residual + off + cout) + b));
+  }
+}
+
 // SPLIT epilogue, part 1: add one chunk's 128 x BN accumulator (TMEM) into the thread's fp32 registers (round to nearest).
 template <int BN>
 __device__ __forceinline__ void split_chunk_add(uint32_t taddr, float (&accr)[BN], bool first, uint64_t* tmem_full_bar, uint32_t parity) {
@@ -320,6 +334,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       } else {
         float accr[BN];
+        split_prefetch_residual<BN>(args.residual, off, args.Cout, n < args.N);
         const int n_chunks = (args.num_kb + SPLIT_CHUNK_KB - 1) / SPLIT_CHUNK_KB;
         for (int c = 0; c < n_chunks; ++c) {
           split_chunk_add<BN>(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN), accr, c == 0, &tmem_full[acc], acc_phase);
@@ -575,6 +590,7 @@ conv_patch_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constan
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       } else {
         float accr[BN];
+        split_prefetch_residual<BN>(args.residual, off, args.Cout, !(args.debug & 1));
         const int n_chunks = 3 * args.n_cblk;          // per channel block: hi phase = 2 chunks of 9 tiles, lo phase = 1
         for (int c = 0; c < n_chunks; ++c) {
           split_chunk_add<BN>(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN), accr, c == 0, &tmem_full[acc], acc_phase);

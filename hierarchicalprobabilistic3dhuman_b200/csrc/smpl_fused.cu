@@ -22,8 +22,8 @@
 //     plain 1-D bulk copies stage them;
 //   * a work item = one chunk of <= 112 meshes (the N samples of an image) x 6 vertex groups: the chunk's features stay
 //     resident in shared memory (112 KB), the posedirs planes stream through a TMA ring;
-//   * 8 epilogue warps: warp = (TMEM lane quarter, half); a half owns one of the two T accumulators, i.e. every other
-//     4-mesh sub-chunk. Vertices may be re-ordered at create time (a hook for
+//   * 16 epilogue warps: warp = (TMEM lane quarter, half, mesh pair); a half owns one of the two T accumulators, i.e.
+//     every other 4-mesh sub-chunk, and its two warps per quarter take two meshes each. Vertices may be re-ordered at create time (a hook for
 //     layouts whose order scatters the stores; identity for part-ordered models). Skinned vertices leave through a small
 //     per-warp staging buffer as full-sector 8-byte stores (one vertex per lane would otherwise write 4-byte pieces at a
 //     12-byte stride);
@@ -57,15 +57,15 @@ constexpr int TN = MS * 12;                 // T-GEMM N: 48 columns = 4 meshes x
 constexpr int ASUB = 8;                     // meshes per A^T buffer = two T sub-chunks
 constexpr int ATPART = TN * 32 * 2;         // one fp16 part of one T sub-chunk, K padded 24 -> 32: 3,072 B
 constexpr int ABUF_BYTES = 2 * 2 * ATPART;  // [tsub][hi|lo]: 12,288 B
-constexpr int ARING = 3;
+constexpr int ARING = 2;
 constexpr int WPART = GV * 32 * 2;          // one fp16 part of a group's skinning weights [128][32]: 8,192 B
 constexpr int WG_BYTES = 2 * WPART;         // 16,384 B
 constexpr int TCOL0 = 3 * NPMAX;            // TMEM column of the first T accumulator (336); the second follows at + TN
 constexpr int GPI = 6;                      // vertex groups per work item
 constexpr int NRANGE = NGRP / GPI;          // 9
 static_assert(NRANGE * GPI == NGRP, "vertex groups must split evenly into work items");
-constexpr int EPI_WARPS = 8;
-constexpr int THREADS = 384;
+constexpr int EPI_WARPS = 16;                // 4 TMEM lane quarters x 2 T accumulators x 2 mesh pairs of a 4-mesh sub-chunk
+constexpr int THREADS = 128 + EPI_WARPS * 32;   // 640
 
 struct FusedSmem {
   static constexpr int F_OFF = 0;                                              // [hi kb0..3 | lo kb0..3] feature tiles
@@ -74,13 +74,15 @@ struct FusedSmem {
   static constexpr int W_OFF = AT_OFF + ARING * ABUF_BYTES;                    // 200,704
   static constexpr int STG_OFF = W_OFF + WG_BYTES;                             // 217,088
   static constexpr int SUM_OFF = STG_OFF + EPI_WARPS * 2 * 384;                // 223,232
-  static constexpr int BAR_OFF = SUM_OFF + 2 * GV * 16;                        // sums [half][128] float4: 227,328
+  static constexpr int BAR_OFF = SUM_OFF + 4 * GV * 16;                        // sums [half * 2 + pair][128] float4
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
 };
 static_assert(FusedSmem::RING_OFF % 1024 == 0 && FusedSmem::TOTAL <= 232448, "shared memory budget");
 
 struct FusedArgs {
   int M, cs, n_chunks, stats, nsu;   // nsu = A^T buffers (8 meshes) per chunk
+  int debug;                         // timing experiments only (HP3D_FUSED_DEBUG): 1 no vertex stores, 2 no statistics pass, 4 no blend
+                                     // MMAs, 8 no posedirs loads (+4), 16 no skinning arithmetic, 32 no T MMAs
   float inv_scale;
   const uint8_t* AT;         // [n_chunks][nsu][ABUF_BYTES] skinning transforms, fp16 hi/lo, UMMA core-matrix order (smpl_fk_kernel)
   const uint8_t* Wg;         // [NGRP][WG_BYTES] skinning weights of each 128-vertex group, fp16 hi/lo, UMMA core-matrix order
@@ -117,14 +119,41 @@ __device__ __forceinline__ void flush_pair(const EpiCtx& c, float* vertices, int
   __syncwarp();
 }
 
+__device__ __forceinline__ void tmem_ld_32x2(uint32_t taddr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t (&r)[4]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
-smpl_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_constant__ CUtensorMap tmFlo,
-                  const __grid_constant__ CUtensorMap tmPhi, const __grid_constant__ CUtensorMap tmPlo,
-                  const __grid_constant__ FusedArgs args) {
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA tile load delivered to the same shared-memory offset of BOTH CTAs of the pair; each CTA's own barrier (same offset)
+// receives the bytes
+__device__ __forceinline__ void tma_load_2d_mc2(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc2(uint64_t* bar) {      // arrives on the same barrier of both CTAs
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+// CL2 (opt-in, HP3D_SMPL_CLUSTER=1): the kernel runs as 2-CTA clusters. The two CTAs work on two different chunks (images) but
+// walk the SAME vertex groups in lockstep, and every posedirs tile is fetched ONCE for the pair: the CTAs take turns issuing
+// the TMA load, which is multicast into both CTAs' ring stage; a stage is re-filled when BOTH CTAs' MMAs have retired it (their
+// commits are multicast to both CTAs' empty barriers). It halves the L2 -> SMEM stream per SM -- and measured no faster,
+// because that stream is hidden behind the epilogue.
+template <bool CL2>
+__device__ __forceinline__ void smpl_fused_body(const CUtensorMap& tmFhi, const CUtensorMap& tmFlo, const CUtensorMap& tmPhi,
+                                                const CUtensorMap& tmPlo, const FusedArgs& args) {
   using L = FusedSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -143,29 +172,36 @@ smpl_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_consta
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_items = args.n_chunks * NRANGE;
+  // work items: (chunk, range of 6 vertex groups); CL2: the pair takes chunks (2q, 2q + 1) of the same range (an odd chunk
+  // count makes the last pair's second CTA repeat the last chunk: identical values to identical addresses)
+  const int crank = CL2 ? (int)cluster_ctarank() : 0;
+  const int item0 = CL2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, item_step = CL2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int n_items = (CL2 ? (args.n_chunks + 1) / 2 : args.n_chunks) * NRANGE;
+  auto chunk_of = [&](int item) { return CL2 ? min(2 * (item / NRANGE) + crank, args.n_chunks - 1) : item / NRANGE; };
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmFhi); tma_prefetch_desc(&tmFlo); tma_prefetch_desc(&tmPhi); tma_prefetch_desc(&tmPlo); }
   if (warp == 1 && lane == 0) {
     mbar_init(f_full, 1); mbar_init(f_empty, 1);
-    for (int s = 0; s < RING; ++s) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], 1); }
+    for (int s = 0; s < RING; ++s) { mbar_init(&ring_full[s], 1); mbar_init(&ring_empty[s], CL2 ? 2 : 1); }
     mbar_init(blend_full, 1); mbar_init(blend_empty, EPI_WARPS);
     for (int b = 0; b < ARING; ++b) { mbar_init(&a_full[b], 1); mbar_init(&a_empty[b], 1); }
     mbar_init(w_full, 1); mbar_init(w_empty, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], EPI_WARPS / 2); }   // a T buffer belongs to one mesh half
+    for (int b = 0; b < 2; ++b) { mbar_init(&t_full[b], 1); mbar_init(&t_empty[b], EPI_WARPS / 2); }   // a T buffer belongs to one half of the warps
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_base_slot);
   tc_fence_before_sync();
   __syncthreads();
+  if (CL2) cluster_sync_all();             // both CTAs' barriers are initialised before any multicast load / commit
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_base_slot;
 
   if (warp == 0) {
     // ===================================================== TMA producer: chunk features (resident per item), posedirs ring
     int stage = 0; uint32_t phase = 0, fphase = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int chunk = item / NRANGE, g0 = (item - chunk * NRANGE) * GPI;
+    unsigned tcount = 0;
+    for (int item = item0; item < n_items; item += item_step) {
+      const int chunk = chunk_of(item), g0 = (item % NRANGE) * GPI;
       mbar_wait(f_empty, fphase ^ 1, 41);
       fphase ^= 1;
       if (elect_one()) mbar_arrive_expect_tx(f_full, 8 * FTILE);
@@ -178,9 +214,16 @@ smpl_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_consta
           for (int kb = 0; kb < KBLKS; ++kb)
             for (int part = 0; part < 2; ++part) {
               mbar_wait(&ring_empty[stage], phase ^ 1, 42);
+              if (args.debug & 8) { if (elect_one()) mbar_arrive(&ring_full[stage]); ++tcount; if (++stage == RING) { stage = 0; phase ^= 1; } continue; }
               if (elect_one()) mbar_arrive_expect_tx(&ring_full[stage], PTILE);
-              if (elect_one()) tma_load_2d(smem + L::RING_OFF + stage * PTILE, part == 0 ? &tmPhi : &tmPlo, &ring_full[stage], kb * 64,
-                                           (g * 3 + plane) * GV);
+              if (!CL2) {
+                if (elect_one()) tma_load_2d(smem + L::RING_OFF + stage * PTILE, part == 0 ? &tmPhi : &tmPlo, &ring_full[stage], kb * 64,
+                                             (g * 3 + plane) * GV);
+              } else if ((int)(tcount & 1u) == crank) {      // the pair's CTAs take turns; the tile lands in both
+                if (elect_one()) tma_load_2d_mc2(smem + L::RING_OFF + stage * PTILE, part == 0 ? &tmPhi : &tmPlo, &ring_full[stage], kb * 64,
+                                                 (g * 3 + plane) * GV);
+              }
+              ++tcount;
               if (++stage == RING) { stage = 0; phase ^= 1; }
             }
     }
@@ -193,8 +236,8 @@ smpl_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_consta
     int tb = 0; uint32_t tphase = 0;
     const uint32_t f_base = smem_u32(smem + L::F_OFF), r_base = smem_u32(smem + L::RING_OFF);
     const uint32_t at_base = smem_u32(smem + L::AT_OFF), w_base = smem_u32(smem + L::W_OFF);
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int chunk = item / NRANGE;
+    for (int item = item0; item < n_items; item += item_step) {
+      const int chunk = chunk_of(item);
       const int cs = min(args.cs, args.M - chunk * args.cs);
       mbar_wait(f_full, fphase, 43);
       fphase ^= 1;
@@ -212,18 +255,18 @@ smpl_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_consta
             mbar_wait(&ring_full[stage], phase, 45);
             tc_fence_after_sync();
             uint64_t pd = umma_desc_sw128(r_base + stage * PTILE);
-            if (elect_one()) {
+            if (!(args.debug & 12) && elect_one()) {
               if (!tail) { umma_f16_x4(d_tmem, pd, fh, idesc, kb != 0 ? 1u : 0u); umma_f16_x4(d_tmem, pd, fl, idesc, 1u); }
               else { umma_f16_x2(d_tmem, pd, fh, idesc, 1u); umma_f16_x2(d_tmem, pd, fl, idesc, 1u); }
             }
-            if (elect_one()) umma_commit(&ring_empty[stage]);
+            if (elect_one()) { if (CL2) umma_commit_mc2(&ring_empty[stage]); else umma_commit(&ring_empty[stage]); }
             if (++stage == RING) { stage = 0; phase ^= 1; }
             // P'_lo tile: P_lo F_hi
             mbar_wait(&ring_full[stage], phase, 45);
             tc_fence_after_sync();
             pd = umma_desc_sw128(r_base + stage * PTILE);
-            if (elect_one()) { if (!tail) umma_f16_x4(d_tmem, pd, fh, idesc, 1u); else umma_f16_x2(d_tmem, pd, fh, idesc, 1u); }
-            if (elect_one()) umma_commit(&ring_empty[stage]);
+            if (!(args.debug & 12) && elect_one()) { if (!tail) umma_f16_x4(d_tmem, pd, fh, idesc, 1u); else umma_f16_x2(d_tmem, pd, fh, idesc, 1u); }
+            if (elect_one()) { if (CL2) umma_commit_mc2(&ring_empty[stage]); else umma_commit(&ring_empty[stage]); }
             if (++stage == RING) { stage = 0; phase ^= 1; }
           }
         }
@@ -241,7 +284,7 @@ smpl_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_consta
             tc_fence_after_sync();
             const uint32_t d_t = tmem_base + (uint32_t)(TCOL0 + tb * TN);
             const uint32_t at = at_base + (uint32_t)(ab * ABUF_BYTES + ts * 2 * ATPART);
-            if (elect_one()) {
+            if (!(args.debug & 32) && elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {           // K = 32 joints (24 used): two K = 16 steps = core-matrix pairs
                 const uint64_t wh = umma_desc_nosw(w_base + ks * 2 * 2048, 2048, 128), wl = umma_desc_nosw(w_base + WPART + ks * 2 * 2048, 2048, 128);
@@ -266,8 +309,8 @@ smpl_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_consta
     // ===================================================== loader of the skinning operands (1-D bulk copies): W per group,
     // A^T per 8 meshes -- both already in UMMA core-matrix order in HBM
     int ab = 0; uint32_t aphase = 0, wphase = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int chunk = item / NRANGE, g0 = (item - chunk * NRANGE) * GPI;
+    for (int item = item0; item < n_items; item += item_step) {
+      const int chunk = chunk_of(item), g0 = (item % NRANGE) * GPI;
       for (int g = g0; g < g0 + GPI; ++g) {
         mbar_wait(w_empty, wphase ^ 1, 51);
         wphase ^= 1;
@@ -283,9 +326,12 @@ smpl_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_consta
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================================================== epilogue: 8 warps = 4 TMEM lane quarters x 2 mesh halves
+    // ===================================================== epilogue: 16 warps = 4 TMEM lane quarters x 2 T accumulators ("half")
+    // x 2 mesh pairs ("sub") of each 4-mesh sub-chunk. The kernel is bound by the latency chain of these warps (TMEM load ->
+    // 12 FMAs -> staging -> stores; profiles/r02v_fused_debug.txt: blend MMAs, posedirs loads and T MMAs are free next to
+    // it), so the warp count, not the arithmetic, sets the speed.
     EpiCtx c;
-    const int quarter = warp & 3, half = (warp - 4) >> 2;
+    const int quarter = warp & 3, half = ((warp - 4) >> 2) & 1, sub = (warp - 4) >> 3;
     c.lane = lane;
     c.stg = reinterpret_cast<float*>(smem + L::STG_OFF) + (warp - 4) * 2 * 96;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -295,8 +341,8 @@ smpl_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_consta
     uint32_t bphase = 0, tphase = 0;
     unsigned kcount = 0;                     // T sub-chunks issued so far: sub-chunk k (global count) lives in T buffer k & 1
 #pragma unroll 1
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int chunk = item / NRANGE, g0 = (item - chunk * NRANGE) * GPI;
+    for (int item = item0; item < n_items; item += item_step) {
+      const int chunk = chunk_of(item), g0 = (item % NRANGE) * GPI;
       c.chunk_base = chunk * args.cs;
       const int cs = min(args.cs, args.M - c.chunk_base);
 #pragma unroll 1
@@ -320,82 +366,83 @@ smpl_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_consta
           tc_fence_after_sync();
           const int m0 = k * MS;
           const int cnt = min(MS, cs - m0);
-          uint32_t t[48], vx[4], vy[4], vz[4];
-          const uint32_t tcol = taddr + (uint32_t)(TCOL0 + half * TN);
+          uint32_t t[24], vx[2], vy[2], vz[2];
+          const uint32_t tcol = taddr + (uint32_t)(TCOL0 + half * TN + sub * 24);
 #pragma unroll
-          for (int q = 0; q < 6; ++q) tmem_ld_32x8(tcol + q * 8, *reinterpret_cast<uint32_t(*)[8]>(&t[q * 8]));
-          tmem_ld_32x4(taddr + (uint32_t)m0, vx);
-          tmem_ld_32x4(taddr + (uint32_t)(NPMAX + m0), vy);
-          tmem_ld_32x4(taddr + (uint32_t)(2 * NPMAX + m0), vz);
+          for (int q = 0; q < 3; ++q) tmem_ld_32x8(tcol + q * 8, *reinterpret_cast<uint32_t(*)[8]>(&t[q * 8]));
+          tmem_ld_32x2(taddr + (uint32_t)(m0 + 2 * sub), vx[0], vx[1]);
+          tmem_ld_32x2(taddr + (uint32_t)(NPMAX + m0 + 2 * sub), vy[0], vy[1]);
+          tmem_ld_32x2(taddr + (uint32_t)(2 * NPMAX + m0 + 2 * sub), vz[0], vz[1]);
           tmem_ld_wait();
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(&t_empty[half]);    // T is in registers: the MMAs of this half's next sub-chunk may start
+          if (2 * sub < cnt && !(args.debug & 16)) {
+            const bool two = 2 * sub + 1 < cnt;
+            float o[6];
 #pragma unroll
-          for (int pr = 0; pr < 2; ++pr) {
-            if (2 * pr < cnt) {
-              const bool two = 2 * pr + 1 < cnt;
-              float o[6];
+            for (int j = 0; j < 2; ++j) {
+              const float x = fmaf(__uint_as_float(vx[j]), inv_scale, vt.x);
+              const float y = fmaf(__uint_as_float(vy[j]), inv_scale, vt.y);
+              const float z = fmaf(__uint_as_float(vz[j]), inv_scale, vt.z);
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const int mm = 2 * pr + j;
-                const float x = fmaf(__uint_as_float(vx[mm]), inv_scale, vt.x);
-                const float y = fmaf(__uint_as_float(vy[mm]), inv_scale, vt.y);
-                const float z = fmaf(__uint_as_float(vz[mm]), inv_scale, vt.z);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                  const float* T = reinterpret_cast<const float*>(&t[mm * 12 + i * 4]);
-                  o[j * 3 + i] = fmaf(T[2], z, fmaf(T[1], y, T[0] * x)) + T[3];
-                }
+              for (int i = 0; i < 3; ++i) {
+                const float* T = reinterpret_cast<const float*>(&t[j * 12 + i * 4]);
+                o[j * 3 + i] = fmaf(T[2], z, fmaf(T[1], y, T[0] * x)) + T[3];
               }
-              if (!two) { o[3] = 0.f; o[4] = 0.f; o[5] = 0.f; }
-              sx += o[0] + o[3]; sy += o[1] + o[4]; sz += o[2] + o[5];
-              float* s = c.stg + 3 * lane;
-              s[0] = o[0]; s[1] = o[1]; s[2] = o[2];
-              s[96] = o[3]; s[97] = o[4]; s[98] = o[5];
-              flush_pair(c, vertices, m0 + 2 * pr, two, tbase, tcnt, orig, valid);
             }
+            if (!two) { o[3] = 0.f; o[4] = 0.f; o[5] = 0.f; }
+            sx += o[0] + o[3]; sy += o[1] + o[4]; sz += o[2] + o[5];
+            float* s = c.stg + 3 * lane;
+            s[0] = o[0]; s[1] = o[1]; s[2] = o[2];
+            s[96] = o[3]; s[97] = o[4]; s[98] = o[5];
+            if (!(args.debug & 1)) flush_pair(c, vertices, m0 + 2 * sub, two, tbase, tcnt, orig, valid);
           }
         }
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(blend_empty);         // v_posed accumulators free: the next group's MMAs overlap the statistics
         if (args.stats) {
-          float4* mine = sums + half * GV + quarter * 32 + lane;
-          float4* other = sums + (half ^ 1) * GV + quarter * 32 + lane;
+          const int part = half * 2 + sub;                  // 4 partial sums per vertex
+          float4* mine = sums + part * GV + quarter * 32 + lane;
           *mine = make_float4(sx, sy, sz, 0.f);
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          const float4 o = *other;
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+          float tx = 0.f, ty = 0.f, tz = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { const float4 o = sums[q * GV + quarter * 32 + lane]; tx += o.x; ty += o.y; tz += o.z; }
           const float inv_n = 1.0f / (float)cs;
-          const float mx = (sx + o.x) * inv_n, my = (sy + o.y) * inv_n, mz = (sz + o.z) * inv_n;
+          const float mx = tx * inv_n, my = ty * inv_n, mz = tz * inv_n;
           // pass 2: mean distance to the mean over this warp's meshes, re-read from L2 (written by this warp a moment ago)
           float dsum = 0.f;
-          if (valid) {
+          if (valid && !(args.debug & 2)) {
 #pragma unroll 1
-            for (int k = k0; k < nT; k += 4) {           // two of this warp's sub-chunks = 8 meshes per iteration: 24 loads in flight
+            for (int k = k0; k < nT; k += 8) {           // four of this warp's sub-chunks = 8 meshes per iteration: 24 loads in flight
               float px[8], py[8], pz[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
-                const int m = (k + 2 * (u >> 2)) * MS + (u & 3);
+                const int m = (k + 2 * (u >> 1)) * MS + 2 * sub + (u & 1);
                 const float* v = vertices + (size_t)(c.chunk_base + min(m, cs - 1)) * NV3 + 3 * orig;
                 px[u] = __ldcg(v); py[u] = __ldcg(v + 1); pz[u] = __ldcg(v + 2);
               }
 #pragma unroll
               for (int u = 0; u < 8; ++u) {
-                const int m = (k + 2 * (u >> 2)) * MS + (u & 3);
+                const int m = (k + 2 * (u >> 1)) * MS + 2 * sub + (u & 1);
                 const float dx = px[u] - mx, dy = py[u] - my, dz = pz[u] - mz;
                 if (m < cs) dsum += sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
               }
             }
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");     // everyone has read the position sums
+          asm volatile("bar.sync 1, 512;" ::: "memory");     // everyone has read the position sums
           mine->w = dsum;
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (half == 0 && valid) {
-            args.unc[(size_t)chunk * NV + orig] = (dsum + other->w) * inv_n;
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+          if (part == 0 && valid) {
+            float d = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) d += sums[q * GV + quarter * 32 + lane].w;
+            args.unc[(size_t)chunk * NV + orig] = d * inv_n;
             if (args.mean) { float* mo = args.mean + ((size_t)chunk * NV + orig) * 3; mo[0] = mx; mo[1] = my; mo[2] = mz; }
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");     // the sums buffer may be rewritten by the next group
+          asm volatile("bar.sync 1, 512;" ::: "memory");     // the sums buffer may be rewritten by the next group
         }
         kcount += (unsigned)nT;
       }
@@ -403,7 +450,21 @@ smpl_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_consta
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (CL2) cluster_sync_all();             // the peer may still multicast into this CTA's ring / signal its barriers
   if (warp == 2) { tc_fence_after_sync(); tmem_dealloc<512>(tmem_base); }
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+smpl_fused_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_constant__ CUtensorMap tmFlo,
+                  const __grid_constant__ CUtensorMap tmPhi, const __grid_constant__ CUtensorMap tmPlo,
+                  const __grid_constant__ FusedArgs args) {
+  smpl_fused_body<false>(tmFhi, tmFlo, tmPhi, tmPlo, args);
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+smpl_fused_pair_kernel(const __grid_constant__ CUtensorMap tmFhi, const __grid_constant__ CUtensorMap tmFlo,
+                       const __grid_constant__ CUtensorMap tmPhi, const __grid_constant__ CUtensorMap tmPlo,
+                       const __grid_constant__ FusedArgs args) {
+  smpl_fused_body<true>(tmFhi, tmFlo, tmPhi, tmPlo, args);
 }
 
 // ---------------------------------------------------------------- forward kinematics -> skinning transforms + 24 joints
@@ -750,11 +811,24 @@ int smpl_fused_forward(void* p, const float* betas, int Mb, const float* global_
   rc = rc ? rc : make_tmap_f16(&tmFlo, f_lo, 2, dims, st, box);
   if (rc) return rc;
   a.inv_scale = h->inv_scale;
+  { const char* de = getenv("HP3D_FUSED_DEBUG"); a.debug = de ? atoi(de) : 0; }
   a.AT = AT; a.Wg = h->Wg; a.vt = h->vt; a.tile_base = h->tile_base;
   a.vertices = vertices; a.unc = a.stats ? unc : nullptr; a.mean = a.stats ? mean : nullptr;
-  const int grid = std::min(a.n_chunks * NRANGE, h->num_sms);
-  HP3D_SMEM_OPT_IN(smpl_fused_kernel, FusedSmem::TOTAL);
-  smpl_fused_kernel<<<grid, THREADS, FusedSmem::TOTAL, stream>>>(tmFhi, tmFlo, h->tmPhi, h->tmPlo, a);
+  // HP3D_SMPL_CLUSTER=1: 2-CTA clusters with the posedirs tiles multicast to both CTAs (smpl_fused_pair_kernel). Parity-green
+  // and measured: 2.243 vs 2.253 ms per 25,600 meshes (profiles/r02u_bench_smpl.jsonl) -- no gain, because the posedirs ring is
+  // NOT what bounds the kernel (profiles/r02v_fused_debug.txt: removing the blend MMAs and their loads changes nothing while
+  // the epilogue runs); kept opt-in as the building block for a deeper pipeline.
+  const char* ce = getenv("HP3D_SMPL_CLUSTER");
+  const bool pair = a.n_chunks >= 2 && ce && !strcmp(ce, "1");
+  if (pair) {
+    const int grid = 2 * std::max(1, std::min(((a.n_chunks + 1) / 2) * NRANGE, h->num_sms / 2));
+    HP3D_SMEM_OPT_IN(smpl_fused_pair_kernel, FusedSmem::TOTAL);
+    smpl_fused_pair_kernel<<<grid, THREADS, FusedSmem::TOTAL, stream>>>(tmFhi, tmFlo, h->tmPhi, h->tmPlo, a);
+  } else {
+    const int grid = std::min(a.n_chunks * NRANGE, h->num_sms);
+    HP3D_SMEM_OPT_IN(smpl_fused_kernel, FusedSmem::TOTAL);
+    smpl_fused_kernel<<<grid, THREADS, FusedSmem::TOTAL, stream>>>(tmFhi, tmFlo, h->tmPhi, h->tmPlo, a);
+  }
   rc = launch_status("smpl_fused_kernel");
   if (rc) return rc;
   if (joints) {

@@ -17,7 +17,7 @@ TOL = 1e-4
 
 @pytest.fixture
 def fused_env():
-    old = {k: os.environ.get(k) for k in ("HP3D_SMPL", "HP3D_SMPL_ORDER")}
+    old = {k: os.environ.get(k) for k in ("HP3D_SMPL", "HP3D_SMPL_ORDER", "HP3D_SMPL_CLUSTER")}
     os.environ["HP3D_SMPL"] = "fused"
     yield
     for k, v in old.items():
@@ -61,12 +61,13 @@ def test_fused_forward_matches_oracle(built_lib, fused_env, M, Mb, Mg):
     assert rel_err(out.vertices, st.vertices) < 1e-5 and rel_err(out.joints, st.joints) < 1e-5
 
 
-@pytest.mark.parametrize("B,N", [(3, 100), (5, 8), (2, 112), (2, 17), (3, 5)])
-def test_fused_statistics_match_oracle(built_lib, fused_env, B, N):
+@pytest.mark.parametrize("B,N,cluster", [(3, 100, "0"), (5, 8, "0"), (2, 112, "0"), (2, 17, "0"), (3, 5, "0"), (3, 100, "1"), (4, 33, "1")])
+def test_fused_statistics_match_oracle(built_lib, fused_env, B, N, cluster):
     """per-vertex mean distance to the mean mesh (utils/sampling_utils.py:189-190) out of the SMPL kernel itself"""
     import ctypes
     import hierarchicalprobabilistic3dhuman_b200 as hp
     from hierarchicalprobabilistic3dhuman_b200 import _lib
+    os.environ["HP3D_SMPL_CLUSTER"] = cluster          # "1": 2-CTA clusters, posedirs tiles multicast (odd chunk count: B = 3)
     model = syn.synthetic_smpl_model()
     smpl = hp.SMPL(model=model).cuda()
     M = B * N
