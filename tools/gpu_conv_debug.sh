@@ -3,7 +3,7 @@
 TAG=${1:-r01x}
 OUT=gpurun_out; mkdir -p $OUT
 for d in ${DBG:-0 1 2 4 7}; do
-  HP3D_CONV_DEBUG=$d timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'conv_|stem2' -c 20 --csv --log-file $OUT/${TAG}_convdbg_$d.csv python tools/bench_encoder.py > /dev/null 2>&1
+  HP3D_CONV_DEBUG=$d timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'conv_|stem2' -c 44 --csv --log-file $OUT/${TAG}_convdbg_$d.csv python tools/bench_encoder.py > /dev/null 2>&1
 done
 python - <<'PY'
 import csv,glob,re,collections
