@@ -83,10 +83,11 @@ def traffic_from_profiles(kernel, grid_ctas):
             rows = list(csv.reader(open(path)))
             hdr = rows[0]
             ki, gi, ri, wi = hdr.index("Kernel Name"), hdr.index("Grid Size"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-            unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(rows[1][ri], 1e9)
+            units = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            ur, uw = units.get(rows[1][ri], 1e9), units.get(rows[1][wi], 1e9)         # ncu picks a unit per COLUMN
             for r in rows[2:]:
                 if kernel in r[ki] and r[gi].replace(" ", "").startswith(f"({grid_ctas},"):
-                    return (float(r[ri]) + float(r[wi])) * unit, os.path.relpath(path, ROOT)
+                    return float(r[ri]) * ur + float(r[wi]) * uw, os.path.relpath(path, ROOT)
         except Exception:
             continue
     return None, None
