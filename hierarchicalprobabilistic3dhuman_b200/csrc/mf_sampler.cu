@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(768, 2) mf_sample_kernel(const float* __restri
                                                          const float* __restrict__ V, int B, int J, int N, float b,
                                                          float m_star, uint64_t seed, uint64_t offset, uint64_t image_offset,
                                                          const float* __restrict__ eps_in,
-                                                         const float* __restrict__ w_in, int n_cand, int max_rounds,
+                                                         const float* __restrict__ w_in, int n_cand, int max_rounds, int parts,
                                                          float* __restrict__ R_out, unsigned long long* stats) {
   extern __shared__ __align__(16) float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -58,7 +58,14 @@ __global__ void __launch_bounds__(768, 2) mf_sample_kernel(const float* __restri
   float* tile = smem;                                  // [CHUNK][J*9]
   float4* stage = reinterpret_cast<float4*>(smem + CHUNK * tile_stride) + warp * 64;   // [64] quats per warp
   float* frames = smem + CHUNK * tile_stride + J * 64 * 4 + warp * 20;                   // U_p [9] | V_p [9] per warp
-  for (int img = blockIdx.x; img < B; img += gridDim.x) {
+  // work item = (image, part): `parts` CTAs share an image's N samples (Philox mode only) so that a batch smaller than the
+  // GPU's 2 x #SM CTA slots still fills them -- B = 256 images alone occupy 256 of 296 slots and drain unevenly (54.7 %
+  // achieved occupancy, profiles/r01z_ncu_full_summary.csv); the injected-noise mode keeps one CTA per image because the
+  // reference's "first N accepted" rule runs over ONE candidate sequence.
+  const int per_part = (N + parts - 1) / parts;
+  for (int item = blockIdx.x; item < B * parts; item += gridDim.x) {
+    const int img = item / parts, part = item - img * parts;
+    const int n_begin = part * per_part, n_end = min(N, n_begin + per_part);
     const size_t ij = (size_t)img * J + j;
     // ---- proper SVD factors and envelope parameters (warp-uniform, held by every lane)
     float s0, s1, s2;
@@ -86,8 +93,8 @@ __global__ void __launch_bounds__(768, 2) mf_sample_kernel(const float* __restri
     const float g0 = 1.f, g1 = 1.0f / sqrtf(O1), g2 = 1.0f / sqrtf(O2), g3 = 1.0f / sqrtf(O3);
     int have = 0, round = 0;
     unsigned n_prop = 0, n_acc = 0, n_fail = 0;
-    for (int n0 = 0; n0 < N; n0 += CHUNK) {
-      const int need = min(CHUNK, N - n0);
+    for (int n0 = n_begin; n0 < n_end; n0 += CHUNK) {
+      const int need = min(CHUNK, n_end - n0);
       while (have < need) {
         bool valid, accept = false;
         float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
@@ -107,7 +114,7 @@ __global__ void __launch_bounds__(768, 2) mf_sample_kernel(const float* __restri
           // Philox subsequence = GLOBAL (image, joint, lane): a rank that owns images [image_offset, image_offset + B) of a
           // sharded batch draws exactly what a single GPU would draw for those images (results independent of world size)
           const uint64_t sub = (ij + image_offset * (uint64_t)J) * 32 + lane;
-          const uint64_t cnt = offset + 2ull * (uint64_t)round;
+          const uint64_t cnt = offset + 2ull * ((uint64_t)round + (uint64_t)part * (uint64_t)max_rounds);
           const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
           const uint4 r0 = philox4x32_10(make_uint4((uint32_t)cnt, (uint32_t)(cnt >> 32), (uint32_t)sub, (uint32_t)(sub >> 32)), key);
           const uint4 r1 = philox4x32_10(make_uint4((uint32_t)(cnt + 1), (uint32_t)((cnt + 1) >> 32), (uint32_t)sub, (uint32_t)(sub >> 32)), key);
@@ -209,8 +216,15 @@ extern "C" int hp3d_mf_sample_sharded(const float* U, const float* S, const floa
   HP3D_SMEM_OPT_IN(mf_sample_kernel, 96 * 1024);
   const int n_cand = eps ? oversampling * N : 0;
   const int max_rounds = 64 + 16 * ((N + 31) / 32);     // Philox mode: acceptance >= 0.43 => ~2.3 rounds per 32
-  const int grid = std::min(B, 148 * 2);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int slots = 2 * sms;
+  // Philox mode: split every image's samples over `parts` CTAs of >= 32 samples. `parts` depends on N ONLY -- it decides which
+  // Philox counters a sample consumes, and results must not depend on how many images a rank holds
+  const int parts = eps ? 1 : std::max(1, std::min(N / 32, 4));
+  const int grid = std::min(B * parts, slots);
   mf_sample_kernel<<<grid, J * 32, smem, (cudaStream_t)stream>>>(U, S, V, B, J, N, b, m_star, seed, offset, image_offset, eps, w,
-                                                                 n_cand, max_rounds, R_out, stats);
+                                                                 n_cand, max_rounds, parts, R_out, stats);
   return launch_status("mf_sample_kernel");
 }

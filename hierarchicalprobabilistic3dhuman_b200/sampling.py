@@ -99,7 +99,8 @@ def pose_matrix_fisher_sampling_torch(pose_U, pose_S, pose_V, num_samples, b=1.5
         assert eps.shape == (B, J, oversampling_ratio * num_samples, 4) and w.shape == (B, J, oversampling_ratio * num_samples)
         eps_p, w_p = eps.data_ptr(), w.data_ptr()
     else:
-        seed, off = _rng_seed_offset(dev, 64 + 16 * ((num_samples + 31) // 32))
+        # the kernel may split an image's samples over up to max(1, N // 32) CTAs, each with its own block of Philox counters
+        seed, off = _rng_seed_offset(dev, (64 + 16 * ((num_samples + 31) // 32)) * max(1, num_samples // 32))
     with torch.cuda.device(dev):
         _status.poll(dev)                      # a shortfall reported by an EARLIER launch surfaces here (no sync)
         _lib.check(_lib.lib().hp3d_mf_sample_sharded(U.data_ptr(), S.data_ptr(), V.data_ptr(), B, J, num_samples, float(b),
