@@ -491,6 +491,35 @@ def main_hp3d(args):
     torch.cuda.synchronize()
     smpl_ms = e0.elapsed_time(e1) / reps
 
+    # ---- robustness to the model's vertex order (real SMPL is not ordered by body part): the same call on a copy of the model
+    #      with its vertices shuffled, fused (default) and staged (round-1 kernels: tile-local LBS -> generic fallback)
+    order_ms = {}
+    if world == 1:
+        shuf = hp.SMPL(model=syn.shuffle_smpl_vertices(syn.synthetic_smpl_model(), seed=3, block=1)).to(dev)
+        h_shuf = shuf._handle(dev)
+        old_mode = os.environ.get("HP3D_SMPL")
+        for tag, hh, mode in (("fused, shuffled vertex order", h_shuf, None), ("staged, part-ordered", h_smpl, "staged"),
+                              ("staged, shuffled vertex order", h_shuf, "staged")):
+            if mode: os.environ["HP3D_SMPL"] = mode
+            else: os.environ.pop("HP3D_SMPL", None)
+            ws_o = torch.empty(L.hp3d_smpl_workspace_bytes(hh, M, cbv), dtype=torch.uint8, device=dev)
+            run_o = lambda: _lib.check(L.hp3d_smpl_forward_stats(hh, betas_c.data_ptr(), cbv, gR.data_ptr(), cbv, Rr.data_ptr(), M, N,
+                                                                  verts_local.data_ptr(), joints.data_ptr(), unc_tmp.data_ptr(), None,
+                                                                  ws_o.data_ptr(), ws_o.numel(), _lib.stream_ptr()))
+            for _ in range(2):
+                run_o()
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                run_o()
+            e1.record()
+            torch.cuda.synchronize()
+            order_ms[tag] = e0.elapsed_time(e1) / reps
+            del ws_o
+        if old_mode is None: os.environ.pop("HP3D_SMPL", None)
+        else: os.environ["HP3D_SMPL"] = old_mode
+        del shuf
+
     # ---- the tensor-core side: encoder alone (input cast + stem + pools + 19 convolutions), algorithmic and issued FLOP/s
     for _ in range(3):
         net.encode(x_dev)
@@ -577,7 +606,9 @@ def main_hp3d(args):
                         "h2d_bytes_per_step": int(x_host.numel() * 4),
                         "d2h_bytes_per_step": int(d2h_bytes),
                         "d2h": "mode vertices + sampled joints + sampled rotmats + per-vertex uncertainty",
-                        "overlap": "4-chunk H2D on a copy stream overlapped with the encoder; consecutive steps double-buffered", "ms_per_step": ms_e2e},
+                        "overlap": "4-chunk H2D on a copy stream overlapped with the encoder; consecutive steps double-buffered", "ms_per_step": ms_e2e,
+                        "note": "PCIe-bound (1.21 GB of fp32 proxy representation per rank and step at ~54 GB/s); with N ranks on one host the "
+                                "ranks share the host's memory / PCIe root complexes (22.9 -> 23.4 -> 27.2 -> 57.7 ms at 1/2/4/8 GPUs, profiles/README.md)"},
                 "e2e_from_image": {"value": world * B / (ms_e2e_img * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d_img_bytes,
                                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": ms_e2e_img,
                                    "input": "pinned host RGB crops (B,3,256,256) fp32 + 2D joints + visibility; Canny edges and joint "
@@ -603,7 +634,8 @@ def main_hp3d(args):
                                            "accounting of the staged kernels is 250,272 B/mesh (blend write + LBS 167,592 + statistics re-read)",
                              "tensor_issued_tflops": FUSED_FLOP_PER_MESH * M / (smpl_ms * 1e-3) / 1e12,
                              "tensor_frac_issued": FUSED_FLOP_PER_MESH * M / (smpl_ms * 1e-3) / 1e12 / pk["bf16_tflops"],
-                             "vertex_order": {"reordered_by_dominant_joint": bool(lay[1].value), "tile_joint_sum": lay[2].value, "tile_joint_max": lay[3].value}},
+                             "vertex_order": {"reordered_by_dominant_joint": bool(lay[1].value), "tile_joint_sum": lay[2].value, "tile_joint_max": lay[3].value},
+                             "other_paths_ms": order_ms or None},
                 "roofline_lbs_staged": {"kernel": "lbs_tile_kernel (staged path: SMPL FK + skinning + 90 joints), timed alone", "bound": "hbm", "achieved": achieved,
                              "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                              "traffic": traffic, "traffic_source": (f"{traffic_src}: ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the "

@@ -60,13 +60,13 @@ class HotPathPipeline:
         L, B, N = self.L, self.B, self.N
         with _lib.nvtx("hp3d.head"):
             F, U, S, V, mode, shape_params, glob, cam = self.net.head(feats)
-            loc = shape_params[:, :10].contiguous()
+            self.betas.copy_(shape_params[:, :10])       # one strided copy straight into the (gather) output slice
+            loc = self.betas
             glob_R = rot6d_to_rotmat(glob)
         with _lib.nvtx("hp3d.smpl_mode"):
             out_mode = self.smpl(body_pose=mode, global_orient=glob_R.unsqueeze(1), betas=loc, pose2rot=False)
         with _lib.nvtx("hp3d.mf_sampler"):
             R = pose_matrix_fisher_sampling_torch(U, S, V, N, out=self.rotmats, image_offset=self.image_offset)
-        self.betas.copy_(loc)
         C = len(self.vertex_chunks)
         cb = B // C
         for c, vch in enumerate(self.vertex_chunks):       # images [c*cb, (c+1)*cb): SMPL on cb*N meshes + statistics

@@ -18,37 +18,59 @@ class _StatusRing:
     """Asynchronous shortfall watch. The reference redraws ALL proposals of an (image, joint) pair when fewer than N were
     accepted (utils/sampling_utils.py:50,68-69); the kernel instead draws until N are accepted and gives up only after a
     bound that is never reached in practice (acceptance >= 0.43, 8x / Philox: (64 + N/2) x 32 proposals) -- in which case it
-    fills the remaining samples with the mode and counts the pair in stats[2]. That must not pass silently: every call
-    copies its counter to pinned host memory behind the kernel (no sync), and the NEXT call on the device (or an explicit
-    `check_sampler_status()`) raises if a previous launch reported a shortfall."""
+    fills the remaining samples with the mode and counts the pair in stats[2]. That must not pass silently, and checking
+    must not cost the hot path a sync, an allocation or a fill kernel: every device owns ONE cumulative counter triple (the
+    kernel only ever adds to it) and a small ring of pinned host snapshots; each call copies the counters behind its kernel,
+    and the NEXT call on the device (or an explicit `check_sampler_status()`) raises if the shortfall count has grown."""
+    SLOTS = 8
 
     def __init__(self):
-        self.pending = {}      # device index -> list of (event, pinned tensor)
+        self.dev = {}          # device index -> dict(stats, host ring, events, next slot, last seen fail count)
 
-    def post(self, dev, stats):
-        host = torch.empty(3, dtype=torch.int64).pin_memory()
-        host.copy_(stats, non_blocking=True)
+    def state(self, dev):
+        st = self.dev.get(dev.index)
+        if st is None:
+            st = dict(stats=torch.zeros(3, device=dev, dtype=torch.int64),
+                      host=[torch.zeros(3, dtype=torch.int64).pin_memory() for _ in range(self.SLOTS)],
+                      ev=[None] * self.SLOTS, slot=0, seen=0)
+            self.dev[dev.index] = st
+        return st
+
+    def post(self, dev):
+        st = self.state(dev)
+        i = st["slot"]
+        if st["ev"][i] is not None:
+            st["ev"][i].synchronize()          # ring wrapped around (8 calls without a poll): the oldest snapshot is long done
+            self._check(st, i)
+        st["host"][i].copy_(st["stats"], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
-        self.pending.setdefault(dev.index, []).append((ev, host))
+        st["ev"][i] = ev
+        st["slot"] = (i + 1) % self.SLOTS
+
+    def _check(self, st, i):
+        st["ev"][i] = None
+        fails = int(st["host"][i][2])
+        if fails > st["seen"]:
+            new, st["seen"] = fails - st["seen"], fails
+            raise SamplerShortfall(
+                f"matrix-Fisher sampler: {new} (image, joint) chunk(s) ran out of proposals and were completed with the "
+                f"distribution mode ({int(st['host'][i][1])} accepted of {int(st['host'][i][0])} proposals so far on this device). "
+                "The reference would redraw (utils/sampling_utils.py:68-69).")
 
     def poll(self, dev=None, wait=False):
-        for idx in ([dev.index] if dev is not None else list(self.pending)):
-            keep = []
-            for ev, host in self.pending.get(idx, []):
+        for idx in ([dev.index] if dev is not None else list(self.dev)):
+            st = self.dev.get(idx)
+            if st is None:
+                continue
+            for i in range(self.SLOTS):
+                ev = st["ev"][i]
+                if ev is None:
+                    continue
                 if wait:
                     ev.synchronize()
                 if ev.query():
-                    if int(host[2]) > 0:
-                        self.pending[idx] = []
-                        raise SamplerShortfall(
-                            f"matrix-Fisher sampler: {int(host[2])} (image, joint) chunk(s) ran out of proposals and were "
-                            f"completed with the distribution mode ({int(host[1])} accepted of {int(host[0])} proposals). "
-                            "With injected noise pass more candidates (oversampling_ratio); the reference would redraw "
-                            "(utils/sampling_utils.py:68-69).")
-                else:
-                    keep.append((ev, host))
-            self.pending[idx] = keep
+                    self._check(st, i)
 
 
 _status = _StatusRing()
@@ -91,7 +113,11 @@ def pose_matrix_fisher_sampling_torch(pose_U, pose_S, pose_V, num_samples, b=1.5
         out = torch.empty(B, num_samples, J, 3, 3, device=dev, dtype=torch.float32)
     else:
         assert out.is_contiguous() and out.shape == (B, num_samples, J, 3, 3) and out.dtype == torch.float32
-    stats = torch.zeros(3, device=dev, dtype=torch.int64)
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    # hot path (Philox, no stats requested): the device's cumulative counters -- no allocation, no fill kernel
+    hot = noise is None and not return_stats
+    stats = _status.state(dev)["stats"] if hot else torch.zeros(3, device=dev, dtype=torch.int64)
     eps_p = w_p = None
     seed = off = 0
     if noise is not None:
@@ -113,7 +139,7 @@ def pose_matrix_fisher_sampling_torch(pose_U, pose_S, pose_V, num_samples, b=1.5
                 raise SamplerShortfall(f"injected noise exhausted for {int(stats[2].item())} (image, joint) chunk(s): the reference "
                                        "would redraw a fresh block (utils/sampling_utils.py:68-69); pass more candidates")
         else:
-            _status.post(dev, stats)
+            _status.post(dev)
     return out
 
 
