@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--sm-limit", type=int, default=-1,
                     help="CTAs of the persistent tensor-core kernels (experiment: leave SMs to a co-running NCCL gather; "
                          "-1 / 0 = all SMs, the default -- 116 of 148 brought nothing at 4 GPUs)")
+    ap.add_argument("--vchunks", type=int, default=0,
+                    help="N>1, full gather: image chunks per step whose vertices are gathered separately (0 = policy: 4 for the "
+                         "copy-engine pushes at 2 GPUs, 1 for NCCL -- 13.8 vs 14.7 ms/step at 4 GPUs, profiles/r02l_4gpu_sweep2.txt)")
     ap.add_argument("--gather", default="full", choices=["full", "stats"],
                     help="N>1: all-gather (rotmats, betas, vertices) [configs[3]] or per-image statistics only")
     return ap.parse_args()
@@ -270,7 +273,8 @@ def main_hp3d(args):
     gb = GatherBuffers(B, {"rotmats": (N, 23, 3, 3), "betas": (10,), "uncertainty": (6890,)}, dev, rank=rank, world=world)
     # sample vertices (BASELINE configs[3]): gathered per image chunk so the NVLink transfer of chunk c overlaps the
     # SMPL kernels of chunk c+1; layout (chunk, rank, image-in-chunk, N, 6890, 3)
-    VC = 4 if (full and world > 1 and B % 4 == 0) else 1
+    _vc = args.vchunks or (4 if (args.transport == "p2p" or (args.transport == "auto" and world == 2)) else 1)
+    VC = _vc if (full and world > 1 and B % _vc == 0) else 1
     cbv = B // VC
     # two buffer sets: the NVLink gather of step i also overlaps the encoder of step i+1
     NBUF = 2 if (full and world > 1) else 1
