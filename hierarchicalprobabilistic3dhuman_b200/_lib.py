@@ -15,7 +15,7 @@ EXPORTS = [
     "hp3d_vertex_uncertainty", "hp3d_rank_samples_by_joints2d", "hp3d_mf_sample", "hp3d_mf_sample_sharded",
     "hp3d_head_create", "hp3d_head_destroy", "hp3d_head_workspace_bytes", "hp3d_head_forward",
     "hp3d_encoder_create", "hp3d_encoder_destroy", "hp3d_encoder_workspace_bytes", "hp3d_encoder_forward", "hp3d_encoder_forward_taps",
-    "hp3d_encoder_forward_image", "hp3d_encoder_forward_argmax", "hp3d_crop_affine", "hp3d_heatmap_keypoints", "hp3d_mf_log_norm_constant", "hp3d_canny_edges", "hp3d_joints2d_to_heatmaps", "hp3d_proxy_rep", "hp3d_joints2d_heatmap_argmax", "hp3d_peer_push", "hp3d_peer_push_multicast",
+    "hp3d_encoder_forward_image", "hp3d_encoder_forward_argmax", "hp3d_encoder_forward_f16in", "hp3d_crop_affine", "hp3d_heatmap_keypoints", "hp3d_mf_log_norm_constant", "hp3d_canny_edges", "hp3d_joints2d_to_heatmaps", "hp3d_proxy_rep", "hp3d_joints2d_heatmap_argmax", "hp3d_peer_push", "hp3d_peer_push_multicast",
 ]
 
 
@@ -105,6 +105,8 @@ def lib():
     L.hp3d_mf_log_norm_constant.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p]
     L.hp3d_encoder_forward_argmax.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_float,
                                               c_void_p, c_void_p, c_void_p]
+    L.hp3d_encoder_forward_f16in.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_float,
+                                             c_void_p, c_void_p, c_void_p]
     L.hp3d_peer_push.argtypes = [c_void_p, POINTER(c_void_p), c_int, c_size_t, c_int, c_void_p]
     L.hp3d_peer_push_multicast.argtypes = [c_void_p, c_void_p, c_size_t, c_int, c_void_p]
     _lib = L

@@ -820,8 +820,13 @@ stem2_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ C
 // arg-max): the sample-ranking step (utils/label_conversions.py:127-155) then never re-reads the 1.1 GB of heat-maps.
 // SPLIT: writes the stem's 64-channel split records instead (128 B per pixel, see stem2_kernel):
 //   [A_hi c0..15 | A_hi c0..15 | A_lo c0..15 | A_hi c16,17 | A_hi c16,17 | A_lo c16,17 | 0 x 10]
-template <bool ARGMAX, bool SPLIT>
-__global__ void __launch_bounds__(256) nchw_f32_to_nhwc32_f16_kernel(const float* __restrict__ x, int C, int HW,
+__device__ __forceinline__ float ld_in(const float* p) { return *p; }
+__device__ __forceinline__ float ld_in(const __half* p) { return __half2float(*p); }
+
+// TIN = float (the reference's input type) or __half (opt-in: a host that already holds the proxy representation in fp16
+// halves the bytes over PCIe; the values are then what they are -- their lo halves are zero)
+template <bool ARGMAX, bool SPLIT, typename TIN = float>
+__global__ void __launch_bounds__(256) nchw_f32_to_nhwc32_f16_kernel(const TIN* __restrict__ x, int C, int HW,
                                                                      __half* __restrict__ y, float eps,
                                                                      unsigned long long* __restrict__ keys, float in_scale) {
   // thread = (pixel, 16-channel half): 16 (or C-16) coalesced plane reads -> one full 32-byte sector of the
@@ -830,15 +835,15 @@ __global__ void __launch_bounds__(256) nchw_f32_to_nhwc32_f16_kernel(const float
   const int p = blockIdx.x * 128 + (threadIdx.x & 127);
   const int half_id = threadIdx.x >> 7;               // 0: channels 0..15, 1: channels 16..31 (warp-uniform)
   const bool valid = p < HW;
-  const float* src = x + (size_t)n * C * HW + (valid ? p : 0);
+  const TIN* src = x + (size_t)n * C * HW + (valid ? p : 0);
   __half2 h[8];
   float v[16];
   unsigned candmask = 0;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int c0 = half_id * 16 + 2 * k;
-    v[2 * k] = (valid && c0 < C) ? src[(size_t)c0 * HW] : 0.f;
-    v[2 * k + 1] = (valid && c0 + 1 < C) ? src[(size_t)(c0 + 1) * HW] : 0.f;
+    v[2 * k] = (valid && c0 < C) ? ld_in(src + (size_t)c0 * HW) : 0.f;
+    v[2 * k + 1] = (valid && c0 + 1 < C) ? ld_in(src + (size_t)(c0 + 1) * HW) : 0.f;
     if (ARGMAX) {
       candmask |= (c0 >= 1 && v[2 * k] > eps) ? (1u << (2 * k)) : 0u;       // channels >= C were loaded as 0
       candmask |= (v[2 * k + 1] > eps) ? (2u << (2 * k)) : 0u;
@@ -895,8 +900,8 @@ __global__ void __launch_bounds__(256) nchw_f32_to_nhwc32_f16_kernel(const float
 // thread (pixel p, half hf) converts channel pairs {0..3, 8} (hf = 0) or {4..7} (hf = 1) -- pair k = channels 2k, 2k+1 --
 // into the record words  hi -> k, dup -> 8 + k, lo -> 16 + k  (pair 8: 24 / 25 / 26; 27..31 = 0), the 16-byte chunks of a
 // record XOR-swizzled by the pixel index against bank conflicts; then all 256 threads copy the 16 KB tile out.
-template <bool ARGMAX>
-__global__ void __launch_bounds__(256) nchw_f32_to_split_records_kernel(const float* __restrict__ x, int C, int HW,
+template <bool ARGMAX, typename TIN = float>
+__global__ void __launch_bounds__(256) nchw_f32_to_split_records_kernel(const TIN* __restrict__ x, int C, int HW,
                                                                         __half* __restrict__ y, float eps,
                                                                         unsigned long long* __restrict__ keys, float in_scale) {
   __shared__ __align__(16) uint32_t tile[128 * 32];
@@ -905,7 +910,7 @@ __global__ void __launch_bounds__(256) nchw_f32_to_split_records_kernel(const fl
   const int pl = threadIdx.x & 127, p = p0 + pl;
   const int hf = threadIdx.x >> 7;                    // warp-uniform
   const bool valid = p < HW;
-  const float* src = x + (size_t)n * C * HW + (valid ? p : 0);
+  const TIN* src = x + (size_t)n * C * HW + (valid ? p : 0);
   const int npair = hf == 0 ? 5 : 4;
   float v[10];
   unsigned candmask = 0;
@@ -914,8 +919,8 @@ __global__ void __launch_bounds__(256) nchw_f32_to_split_records_kernel(const fl
     if (i < npair) {
       const int k = hf == 0 ? (i < 4 ? i : 8) : 4 + i;          // channel pair index
       const int c0 = 2 * k;
-      const float a = (valid && c0 < C) ? src[(size_t)c0 * HW] : 0.f;
-      const float b = (valid && c0 + 1 < C) ? src[(size_t)(c0 + 1) * HW] : 0.f;
+      const float a = (valid && c0 < C) ? ld_in(src + (size_t)c0 * HW) : 0.f;
+      const float b = (valid && c0 + 1 < C) ? ld_in(src + (size_t)(c0 + 1) * HW) : 0.f;
       v[2 * i] = a; v[2 * i + 1] = b;
       if (ARGMAX) {
         candmask |= (c0 >= 1 && a > eps) ? (1u << (2 * i)) : 0u;      // channel 0 is the edge map
@@ -1580,7 +1585,7 @@ size_t encoder_tc_workspace_bytes(const void* p, int B, int H, int W) {
 }
 
 int encoder_tc_forward(const void* p, const float* x, int B, int H, int W, float* feats, void* workspace,
-                       size_t workspace_bytes, float* taps, cudaStream_t s, const ImageInput* image, const ArgmaxOut* amax) {
+                       size_t workspace_bytes, float* taps, cudaStream_t s, const ImageInput* image, const ArgmaxOut* amax, bool x_half) {
   const EncoderTc* E = (const EncoderTc*)p;
   if (H != 256 || W != 256) { set_error("the tensor-core encoder supports 256x256 proxy representations (DATA.PROXY_REP_SIZE)"); return -1; }
   const int Bp = (B + 1) & ~1;
@@ -1596,21 +1601,32 @@ int encoder_tc_forward(const void* p, const float* x, int B, int H, int W, float
   if (image) {    // Canny edges + joint heat-maps written straight into the stem's fp16 input records (proxy.cu)
     rc = proxy_rep_nhwc_f16(image->rgb, image->joints2d, image->visibility, B, H, image->gaussian_std, image->gaussian_size,
                             image->threshold, image->nms, image->heat_std, xin, E->split ? 1 : 0, s);
-  } else if (amax) {
-    unsigned long long* keys = (unsigned long long*)((char*)workspace + encoder_tc_workspace_bytes(p, B, H, W) - align_up((size_t)B * 17 * 8, 1024));
-    HP3D_CUDA(cudaMemsetAsync(keys, 0, (size_t)B * 17 * 8, s));
-    if (E->split && env_int("HP3D_CAST", 2) == 2) nchw_f32_to_split_records_kernel<true><<<cgrid, 256, 0, s>>>(x, 18, H * W, xin, amax->eps, keys, in_scale);
-    else if (E->split) nchw_f32_to_nhwc32_f16_kernel<true, true><<<cgrid, 256, 0, s>>>(x, 18, H * W, xin, amax->eps, keys, in_scale);
-    else nchw_f32_to_nhwc32_f16_kernel<true, false><<<cgrid, 256, 0, s>>>(x, 18, H * W, xin, amax->eps, keys, in_scale);
-    rc = launch_status("nchw_f32_to_nhwc32_f16_kernel");
-    if (rc) return rc;
-    argmax_decode_kernel<<<cdiv(B * 17, 128), 128, 0, s>>>(keys, B * 17, W, amax->joints2d_px, amax->vis);
-    rc = launch_status("argmax_decode_kernel");
   } else {
-    if (E->split && env_int("HP3D_CAST", 2) == 2) nchw_f32_to_split_records_kernel<false><<<cgrid, 256, 0, s>>>(x, 18, H * W, xin, 0.f, nullptr, in_scale);
-    else if (E->split) nchw_f32_to_nhwc32_f16_kernel<false, true><<<cgrid, 256, 0, s>>>(x, 18, H * W, xin, 0.f, nullptr, in_scale);
-    else nchw_f32_to_nhwc32_f16_kernel<false, false><<<cgrid, 256, 0, s>>>(x, 18, H * W, xin, 0.f, nullptr, in_scale);
-    rc = launch_status("nchw_f32_to_nhwc32_f16_kernel");
+    // input cast (+ heat-map arg-max as a by-product); x is fp32 NCHW, or fp16 NCHW when x_half
+    unsigned long long* keys = nullptr;
+    const float eps = amax ? amax->eps : 0.f;
+    if (amax) {
+      keys = (unsigned long long*)((char*)workspace + encoder_tc_workspace_bytes(p, B, H, W) - align_up((size_t)B * 17 * 8, 1024));
+      HP3D_CUDA(cudaMemsetAsync(keys, 0, (size_t)B * 17 * 8, s));
+    }
+    const bool staged = E->split && env_int("HP3D_CAST", 2) == 2;
+    const __half* xh = (const __half*)x;
+#define HP3D_CAST_LAUNCH(AM)                                                                                                        \
+    do {                                                                                                                            \
+      if (staged) { if (x_half) nchw_f32_to_split_records_kernel<AM, __half><<<cgrid, 256, 0, s>>>(xh, 18, H * W, xin, eps, keys, in_scale);          \
+                    else nchw_f32_to_split_records_kernel<AM, float><<<cgrid, 256, 0, s>>>(x, 18, H * W, xin, eps, keys, in_scale); }                  \
+      else if (E->split) { if (x_half) nchw_f32_to_nhwc32_f16_kernel<AM, true, __half><<<cgrid, 256, 0, s>>>(xh, 18, H * W, xin, eps, keys, in_scale); \
+                           else nchw_f32_to_nhwc32_f16_kernel<AM, true, float><<<cgrid, 256, 0, s>>>(x, 18, H * W, xin, eps, keys, in_scale); }        \
+      else { if (x_half) nchw_f32_to_nhwc32_f16_kernel<AM, false, __half><<<cgrid, 256, 0, s>>>(xh, 18, H * W, xin, eps, keys, in_scale);             \
+             else nchw_f32_to_nhwc32_f16_kernel<AM, false, float><<<cgrid, 256, 0, s>>>(x, 18, H * W, xin, eps, keys, in_scale); }                     \
+    } while (0)
+    if (amax) HP3D_CAST_LAUNCH(true); else HP3D_CAST_LAUNCH(false);
+#undef HP3D_CAST_LAUNCH
+    rc = launch_status("proxy representation cast kernel");
+    if (!rc && amax) {
+      argmax_decode_kernel<<<cdiv(B * 17, 128), 128, 0, s>>>(keys, B * 17, W, amax->joints2d_px, amax->vis);
+      rc = launch_status("argmax_decode_kernel");
+    }
   }
   if (rc) return rc;
   rc = run_tc_conv(E, E->stem, xin, B, H, W, nullptr, 1, stem, s);

@@ -309,6 +309,19 @@ extern "C" int hp3d_encoder_forward_argmax(const hp3d_encoder* h, const float* x
   return hp3d_encoder_forward_taps(h, x, B, H, W, feats, workspace, workspace_bytes, nullptr, stream_);
 }
 
+extern "C" int hp3d_encoder_forward_f16in(const hp3d_encoder* h, const void* x_f16, int B, int H, int W, float* feats,
+                                          void* workspace, size_t workspace_bytes, float eps, float* joints2d_px,
+                                          int32_t* vis, void* stream_) {
+  HP3D_ARG(h && x_f16 && feats && workspace, "null argument");
+  HP3D_ARG(h->mode != HP3D_ENC_PARITY, "fp16 input needs a tensor-core handle (HP3D_ENC_SPLIT / HP3D_ENC_FAST)");
+  HP3D_ARG((joints2d_px == nullptr) == (vis == nullptr), "joints2d_px and vis must be given together");
+  HP3D_ARG(B > 0 && H >= 32 && W >= 32 && H % 32 == 0 && W % 32 == 0, "H and W must be multiples of 32");
+  HP3D_ARG(workspace_bytes >= hp3d_encoder_workspace_bytes(h, B, H, W), "workspace too small");
+  const ArgmaxOut am = {eps, joints2d_px, vis};
+  return encoder_tc_forward(h->tc, (const float*)x_f16, B, H, W, feats, workspace, workspace_bytes, nullptr, (cudaStream_t)stream_,
+                            nullptr, joints2d_px ? &am : nullptr, true);
+}
+
 extern "C" int hp3d_encoder_forward_taps(const hp3d_encoder* h, const float* x, int B, int H, int W, float* feats,
                                          void* workspace, size_t workspace_bytes, float* taps, void* stream_) {
   HP3D_ARG(h && x && feats && workspace, "null argument");

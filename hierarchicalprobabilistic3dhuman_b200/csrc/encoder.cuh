@@ -16,7 +16,7 @@ struct ImageInput {
 struct ArgmaxOut { float eps; float* joints2d_px; int* vis; };
 int encoder_tc_forward(const void* p, const float* x_nchw, int B, int H, int W, float* feats, void* workspace,
                        size_t workspace_bytes, float* taps, cudaStream_t stream, const ImageInput* image = nullptr,
-                       const ArgmaxOut* argmax = nullptr);
+                       const ArgmaxOut* argmax = nullptr, bool x_half = false);
 // rank.cu: stand-alone heat-map arg-max (17 maps per image, images `image_stride` floats apart)
 int heatmap_argmax(const float* heatmaps, long long image_stride, int B, int H, int W, float eps, float* joints2d_px,
                    int* vis, cudaStream_t stream);

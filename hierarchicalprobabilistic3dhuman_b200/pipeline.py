@@ -109,18 +109,18 @@ class HotPathPipeline:
 
     # ------------------------------------------------------------------ host-streaming pass
     def _staging(self, x_host=None):
-        if self._stage is not None and x_host is not None and self._stage["x"] is None:
-            self._stage["x"] = [torch.empty_like(x_host, device=self.dev) for _ in range(2)]
         if self._stage is None:
             B, dev = self.B, self.dev
             mk_host = lambda *s: torch.empty(*s, dtype=torch.float32).pin_memory()
             self._stage = dict(
-                x=[torch.empty_like(x_host, device=dev) for _ in range(2)] if x_host is not None else None,
+                x={},                                                  # input dtype -> two device staging buffers
                 x_free=[None, None],                                   # event: encoder finished reading slot
                 out=[dict(mode_vertices=mk_host(B, 6890, 3), joints=mk_host(B * self.N, 90, 3),
                           rotmats=mk_host(B, self.N, 23, 3, 3), uncertainty=mk_host(B, 6890)) for _ in range(2)],
                 out_done=[None, None],                                  # event: D2H of slot finished
                 h2d=torch.cuda.Stream(device=dev), d2h=torch.cuda.Stream(device=dev))
+        if x_host is not None and x_host.dtype not in self._stage["x"]:
+            self._stage["x"][x_host.dtype] = [torch.empty_like(x_host, device=self.dev) for _ in range(2)]
         return self._stage
 
     def release_host_vertices(self):
@@ -130,7 +130,7 @@ class HotPathPipeline:
                 o.pop("vertices", None)
 
     def run_host(self, x_host, return_vertices=False):
-        """x_host: pinned (B,18,256,256) fp32 HOST tensor. Returns (dict of pinned host result tensors, event);
+        """x_host: pinned (B,18,256,256) fp32 (or, opt-in, fp16) HOST tensor. Returns (dict of pinned host result tensors, event);
         the results are valid once `event.synchronize()` returns. Calls may be issued back to back: copies of
         call i+1 overlap the kernels of call i. `return_vertices=True` also copies the (B,N,6890,3) sampled vertices back
         (8.3 MB per image: the reference's consumer keeps them on the device, predict/...:157-165)."""
@@ -150,7 +150,7 @@ class HotPathPipeline:
         cb = B // C
         with torch.cuda.device(self.dev):
             main = torch.cuda.current_stream()
-            xbuf = st["x"][slot]
+            xbuf = st["x"][x_host.dtype][slot]     # fp32 (the reference's input type) or fp16 (opt-in: half the PCIe bytes)
             evs = []
             with torch.cuda.stream(st["h2d"]):
                 if st["x_free"][slot] is not None:

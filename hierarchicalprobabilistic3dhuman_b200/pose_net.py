@@ -157,12 +157,15 @@ class PoseMFShapeGaussianNet(nn.Module):
     def encode(self, input, return_joints2d=False, eps=1e-6):
         """(B,18,H,W) fp32 NCHW on CUDA -> (B,512) features (reference models/resnet.py:202-217).
         return_joints2d=True additionally returns the arg-max pixel (B,17,2) and visibility (B,17) int32 of the joint
-        heat-maps in channels 1..17 (utils/label_conversions.py:127-155), a by-product of the input pass."""
+        heat-maps in channels 1..17 (utils/label_conversions.py:127-155), a by-product of the input pass.
+        A torch.float16 input is consumed as it is by the tensor-core modes (opt-in: half the bytes over PCIe for a host that
+        holds the proxy representation in fp16; the values are then fp16's); every other dtype is converted to float32."""
         _lib.require_cuda(input, "input")
         dev = input.device
         key = dev.index if dev.index is not None else torch.cuda.current_device()
         enc, _ = self._build_handles(key, True)
-        x = input.detach().to(torch.float32).contiguous()
+        half_in = input.dtype == torch.float16 and self.encoder_mode != "parity"
+        x = input.detach().contiguous() if half_in else input.detach().to(torch.float32).contiguous()
         B, C, H, W = x.shape
         assert C == 18
         L = _lib.lib()
@@ -170,6 +173,14 @@ class PoseMFShapeGaussianNet(nn.Module):
         with torch.cuda.device(dev):
             nbytes = L.hp3d_encoder_workspace_bytes(enc, B, H, W)
             ws = self._ws.get(nbytes, dev)
+            if half_in:
+                j2d = torch.empty(B, 17, 2, device=dev, dtype=torch.float32) if return_joints2d else None
+                vis = torch.empty(B, 17, device=dev, dtype=torch.int32) if return_joints2d else None
+                _lib.check(L.hp3d_encoder_forward_f16in(enc, x.data_ptr(), B, H, W, feats.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                        float(eps), j2d.data_ptr() if return_joints2d else None,
+                                                        vis.data_ptr() if return_joints2d else None, _lib.stream_ptr()),
+                           "hp3d_encoder_forward_f16in")
+                return (feats, j2d, vis) if return_joints2d else feats
             if return_joints2d:
                 j2d = torch.empty(B, 17, 2, device=dev, dtype=torch.float32)
                 vis = torch.empty(B, 17, device=dev, dtype=torch.int32)

@@ -220,6 +220,13 @@ int hp3d_encoder_forward(const hp3d_encoder* h, const float* x_nchw, int B, int 
 int hp3d_encoder_forward_argmax(const hp3d_encoder* h, const float* x_nchw, int B, int H, int W, float* feats,
                                 void* workspace, size_t workspace_bytes, float eps, float* joints2d_px, int32_t* vis,
                                 void* stream);
+/* hp3d_encoder_forward / _argmax for a proxy representation the caller already holds in fp16 (x_nchw_f16 [B*18*H*W] halves;
+ * tensor-core handles only). Opt-in: it halves the bytes a host has to push over PCIe (the fp32 contract input makes the
+ * end-to-end path PCIe-bound); the arithmetic is unchanged, the input values are whatever fp16 holds. joints2d_px / vis may
+ * both be NULL (no arg-max by-product). */
+int hp3d_encoder_forward_f16in(const hp3d_encoder* h, const void* x_nchw_f16, int B, int H, int W, float* feats,
+                               void* workspace, size_t workspace_bytes, float eps, float* joints2d_px, int32_t* vis,
+                               void* stream);
 /* image-space entry (tensor-core handles only: HP3D_ENC_SPLIT / HP3D_ENC_FAST): rgb [B*3*256*256] in [0,1], joints2d [B*17*2], visibility [B*17]
  * bytes or NULL -> feats. The Canny + heat-map kernel writes the stem's fp16 NHWC input records directly: the fp32
  * proxy representation of predict/...:100 never exists in memory. Same workspace as hp3d_encoder_forward. */

@@ -89,3 +89,24 @@ def test_tensor_core_batch_invariance(built_lib, mode):
     f5 = m.encode(x)
     f1 = torch.cat([m.encode(x[i:i + 1]) for i in range(5)])
     assert torch.equal(f5, f1)
+
+
+def test_fp16_host_input_option(built_lib):
+    """Opt-in fp16 proxy representation (hp3d_encoder_forward_f16in): the same arithmetic on the values fp16 holds -- bit-identical
+    to feeding those values as fp32, and within the contract of the oracle run on them; the effect of rounding the INPUT to fp16
+    (not part of the contract) is reported with its own bound."""
+    sd = syn.synthetic_state_dict(0)
+    x = torch.from_numpy(syn.synthetic_proxy_rep(3, seed=4))
+    x16 = x.half()
+    with torch.no_grad():
+        ref16 = net_oracle.encoder_forward(sd, x16.float())
+        ref32 = net_oracle.encoder_forward(sd, x)
+    for mode in ("split", "fast"):
+        m = make_model(mode)
+        f16, j16, v16 = m.encode(x16.cuda(), return_joints2d=True)
+        f32, j32, v32 = m.encode(x16.float().cuda(), return_joints2d=True)
+        assert torch.equal(f16, f32) and torch.equal(j16, j32) and torch.equal(v16, v32)
+        assert torch.equal(m.encode(x16.cuda()), f16)
+        if mode == "split":
+            assert rel_err(f16, ref16) < 1e-4
+            assert rel_err(f16, ref32) < 2e-3          # input rounding, measured ~1e-4
