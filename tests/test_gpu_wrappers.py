@@ -153,3 +153,28 @@ def test_sampler_shortfall_is_reported_not_silent(built_lib):
     # Philox mode: the asynchronous status ring reports nothing for a healthy launch
     hp.pose_matrix_fisher_sampling_torch(U, S, V, N)
     hp.check_sampler_status()
+
+
+def test_batched_composition_with_sampled_betas(built_lib):
+    """train/train_poseMF_shapeGaussian_net.py:293-308: B images x N samples in one SMPL call with per-sample betas
+    (`Normal.sample([N])` transposed to image-major) and the global orientation expanded per image."""
+    import hierarchicalprobabilistic3dhuman_b200 as hp
+    model = syn.synthetic_smpl_model()
+    smpl = hp.SMPL(model=model).cuda()
+    B, N = 3, 6
+    U, S, V = _usv(B, 14)
+    dist = torch.distributions.Normal(torch.randn(B, 10, device="cuda"), torch.rand(B, 10, device="cuda") * 0.3 + 0.05)
+    glob_R = hp.rot6d_to_rotmat(torch.randn(B, 6, device="cuda"))
+    torch.manual_seed(21)
+    res = hp.sample_meshes_batched(U, S, V, dist, glob_R, N, smpl, use_mean_shape=False)
+    betas = res["betas"]                                             # (B*N, 10), image-major
+    assert betas.shape == (B * N, 10) and (betas[0] - betas[1]).abs().max() > 1e-3
+    ref = SMPLOracle(model, torch.float64).forward(betas.cpu(), res["rotmats"].cpu().view(B * N, 23, 3, 3),
+                                                   glob_R.cpu().repeat_interleave(N, 0)[:, None])
+    v_ref = ref["vertices"].view(B, N, 6890, 3)
+    assert rel_err(res["vertices"], v_ref) < TOL and rel_err(res["joints"], ref["joints"].view(B, N, 90, 3)) < TOL
+    u_ref = (v_ref - v_ref.mean(1, keepdim=True)).norm(dim=-1).mean(1)
+    assert rel_err(res["per_vertex_uncertainty"], u_ref) < TOL and rel_err(res["mean_vertices"], v_ref.mean(1)) < TOL
+    # the sampled rotations are proper rotations
+    R = res["rotmats"]
+    assert (torch.linalg.det(R) - 1).abs().max() < 1e-5
