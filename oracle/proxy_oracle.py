@@ -55,8 +55,11 @@ SOBEL = ((1, 0, -1), (2, 0, -2), (1, 0, -1))                         # canny_edg
 NMS_NEIGHBOUR = ((0, 1), (1, 1), (1, 0), (1, -1), (0, -1), (-1, -1), (-1, 0), (-1, 1))
 
 
-def canny_edges(img, threshold=0.0, non_max_suppression=True, gaussian_filter_std=1.0, gaussian_filter_size=5):
-    """img (B,C,H,W) float32 -> dict with the reference's keys (each (B,1,H,W) except blurred_img (B,C,H,W))."""
+def canny_edges(img, threshold=0.0, non_max_suppression=True, gaussian_filter_std=1.0, gaussian_filter_size=5,
+                return_gradients=False):
+    """img (B,C,H,W) float32 -> dict with the reference's keys (each (B,1,H,W) except blurred_img (B,C,H,W)).
+    return_gradients=True adds the channel-averaged Sobel responses "grad_x", "grad_y" (B,1,H,W) (not reference outputs: test
+    helpers, so a checker can form the magnitude in float64 instead of relying on the host's vector pow)."""
     img = img.float()
     B, C, H, W = img.shape
     g = gaussian_taps(gaussian_filter_size, gaussian_filter_std)
@@ -78,6 +81,8 @@ def canny_edges(img, threshold=0.0, non_max_suppression=True, gaussian_filter_st
     thr_mag[mag < threshold] = 0.0
     out = {"blurred_img": blurred_img, "grad_magnitude": mag[:, None], "grad_orientation": ori[:, None],
            "thresholded_grad_magnitude": thr_mag[:, None]}
+    if return_gradients:
+        out["grad_x"], out["grad_y"] = gx[:, None], gy[:, None]
     if non_max_suppression:
         idx = (ori / 45) % 8
         thin = mag.clone()
