@@ -51,6 +51,13 @@ def _worker(rank, world, port, q):
         sp = SymmPush((2, world, 3, 5), "cpu", rank, world)
         ok &= (not sp.ok) and tuple(sp.full.shape) == (2, world, 3, 5) and sp.error is not None
         sp.push(lambda buf: buf[0, rank], None)
+        # the completion fence runs on a communicator of its OWN (bench.py: collectives issued on the comm stream must not share
+        # ProcessGroupNCCL's internal stream with the main stream's collectives): the group is plumbed through and used
+        own = dist.new_group(backend="gloo")
+        sp2 = SymmPush((2, world, 3, 5), "cpu", rank, world, mode="ce", fence_group=own)
+        sp2.flag.fill_(float(rank + 1))
+        dist.all_reduce(sp2.flag, group=sp2.fence_group)           # what SymmPush.fence() issues (on a CUDA stream there)
+        ok &= sp2.fence_group is own and float(sp2.flag) == sum(range(1, world + 1)) and sp2.mode == "ce"
         q.put((rank, ok, gb.bytes_received_per_rank(["vertices"])))
     finally:
         dist.destroy_process_group()
